@@ -1,0 +1,231 @@
+/*
+ * rtrec_b200.h -- C-ABI of the B200-native SLIM hot path (librtrec_b200.so).
+ *
+ * The reference (myui/rtrec 0.2.7, pure Python) has no FFI of its own; the seam this library
+ * replaces is the pair of Python classes that `rtrec.models.SLIM` composes:
+ *   - the store    `UserItemInteractions`  (/root/reference/rtrec/utils/interactions.py:14-353)
+ *   - the operator `SLIMElastic`           (/root/reference/rtrec/models/internal/slim_elastic.py:156-857)
+ * Each entry point below cites the reference lines it replaces.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; rt_last_error() gives the message
+ *     (thread-local).  No exceptions cross the boundary, no torch types in signatures.
+ *   - pointers named d_* are DEVICE pointers (cudaMalloc / torch CUDA tensors), h_* are HOST
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     All device work is enqueued on that stream; functions do not synchronise unless stated.
+ *   - matrices: float32 values, int32 indices/offsets (the reference builds float32/int32 scipy
+ *     matrices, interactions.py:276,303).  CSR = (rptr[n_rows+1], ridx, rval), CSC likewise.
+ *   - temporary device storage is owned by the library (grow-only arenas, rt_release_scratch());
+ *     use one caller thread per process and keep calls stream-ordered, as the reference's
+ *     single-threaded Python does (SURVEY.md 8b "Threading").
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef RTREC_B200_H
+#define RTREC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define RT_OK 0
+#define RT_ERR_ARG (-1)
+#define RT_ERR_CUDA (-2)
+#define RT_ERR_CAPACITY (-3) /* an output buffer was too small; sizes needed are reported */
+#define RT_ERR_NO_DEVICE (-4)
+
+int rt_version(void);
+const char *rt_last_error(void);
+/* number of SMs / bytes of opt-in shared memory per block of the current device (<0 on error) */
+int rt_device_info(int *sm_count, int *smem_optin_bytes, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Interaction store  (replaces interactions.py:81-119 add_interaction, :62-79 _apply_decay,
+ * :259-303 to_csr/to_csc).  State = three device arrays sorted by key = (user << 32 | item):
+ *   keys u64[n_pairs], vals f64[n_pairs] (stored rating), stamps f64[n_pairs] (last timestamp).
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * Fold one batch of events (arrival order) into the store.  Semantics per event k, exactly as
+ * add_interaction (interactions.py:99-111):
+ *   T_k = max(max_ts_in, max_{m<=k}(ts_m + 1));
+ *   upsert: (val, stamp) <- (delta_k, ts_k)                      [no clipping]
+ *   else  : cur = 0 if pair absent or stored val == 0 else val * rate^((T_k - stamp)/86400)
+ *           (val, stamp) <- (clip(cur + delta_k, min_value, max_value), ts_k)
+ * decay_rate <= 0 or NaN means "no decay" (decay_rate is None in the reference).
+ * Inputs d_users/d_items int32, d_ts f64, d_delta f64.  The merged store is written to
+ * d_out_* (capacity out_cap pairs, must be >= n_pairs + n_events); *h_n_out receives the new
+ * pair count, *h_max_ts/-user/-item the running maxima (max_ts_in etc. are the carried-in
+ * values; max ids start at 0 like interactions.py:40-41).  Synchronises the stream.
+ */
+int rt_store_fold(const int32_t *d_users, const int32_t *d_items, const double *d_ts,
+                  const double *d_delta, int64_t n_events, int upsert, double min_value,
+                  double max_value, double decay_rate, const uint64_t *d_keys, const double *d_vals,
+                  const double *d_stamps, int64_t n_pairs, double max_ts_in, int32_t max_user_in,
+                  int32_t max_item_in, uint64_t *d_out_keys, double *d_out_vals, double *d_out_stamps,
+                  int64_t out_cap, int64_t *h_n_out, double *h_max_ts, int32_t *h_max_user,
+                  int32_t *h_max_item, void *stream);
+
+/*
+ * Build the float32 CSR and CSC interaction matrices from the store (to_csr / to_csc,
+ * interactions.py:259-303): x = f32(val * rate^((max_ts - stamp)/86400)), shape
+ * (n_users, n_items) = (max_user_id+1, max_item_id+1); explicit zeros are kept.
+ * d_item_mask (optional, uint8[n_items]) restricts the matrices to the flagged item columns
+ * (to_csc(select_items), interactions.py:296).  Outputs have capacity n_pairs entries;
+ * d_ccol (optional, int32[n_pairs]) receives the column id of every CSC entry (COO view used
+ * by the Gram kernel).  *h_nnz = number of entries kept, *h_nonneg = 1 iff all kept values
+ * are >= 0.  Synchronises the stream.
+ */
+int rt_store_build(const uint64_t *d_keys, const double *d_vals, const double *d_stamps,
+                   int64_t n_pairs, double decay_rate, double max_ts, int32_t n_users, int32_t n_items,
+                   const uint8_t *d_item_mask, int32_t *d_rptr, int32_t *d_ridx, float *d_rval,
+                   int32_t *d_cptr, int32_t *d_cidx, float *d_cval, int32_t *d_ccol, int64_t *h_nnz,
+                   int *h_nonneg, void *stream);
+
+/* Point lookup of stored (val, stamp) for n (user,item) queries; found[q]=0 if absent.
+ * (get_user_item_rating, interactions.py:134-149, without the decay which the host applies.) */
+int rt_store_lookup(const uint64_t *d_keys, const double *d_vals, const double *d_stamps, int64_t n_pairs,
+                    const uint64_t *d_query, int64_t n, double *d_val_out, double *d_stamp_out,
+                    uint8_t *d_found, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fit  (replaces SLIMElastic.fit / fit_in_parallel / partial_fit_items, slim_elastic.py:229-564,
+ * FeatureSelectionWrapper.fit :139-154 and sklearn's sparse_enet_coordinate_descent)
+ * ---------------------------------------------------------------------------------------- */
+
+/*
+ * Item-item Gram rows.  For every stored entry e of the CSC/COO view (column j = d_ccol[e],
+ * user u = d_cidx[e], value y = d_cval[e]) adds y * X[u, :] into row j of G (ld = ldg floats).
+ * Row j of G is then X^T x_j, which is both the feature-score vector of target j
+ * (slim_elastic.py:141, X.T.dot(y)) and row j of the Gram matrix the solver replays on.
+ * G must be zero-filled by the caller for the rows being produced.  Entries [e_begin, e_end)
+ * only are processed (lets callers shard by item range across GPUs / build row subsets).
+ */
+int rt_gram_rows(const int32_t *d_ccol, const int32_t *d_cidx, const float *d_cval, int64_t e_begin,
+                 int64_t e_end, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                 float *d_G, int64_t ldg, void *stream);
+
+typedef struct {
+    double alpha;        /* SLIMElastic.alpha      (slim_elastic.py:184) */
+    double l1_ratio;     /* SLIMElastic.l1_ratio   (:185) */
+    double tol;          /* :188 */
+    int32_t max_iter;    /* :187 */
+    int32_t positive;    /* positive_only :186 */
+    uint32_t seed;       /* RandomState(random_state).randint(0, 2^31-1), _cd_fast.pyx:748 */
+    int32_t nn;          /* nn_feature_selection (:190), 0 = all items are features */
+    int32_t n_samples;   /* rows of X = max_user_id+1; scales the penalties (_coordinate_descent.py:781) */
+    int32_t nonneg;      /* 1 iff every stored value of X is >= 0 (enables live-set pruning) */
+} rt_fit_config;
+
+/* xorshift32 draw table: out[t] = value of the (t+1)-th our_rand_r call from `seed`
+ * (sklearn/utils/_random.pxd:20-34).  The sequence is identical for every column. */
+int rt_rng_table(uint32_t seed, int64_t n, uint32_t *d_out, void *stream);
+
+/*
+ * Solve the ElasticNet problems of `n_targets` target columns on the Gram matrix.
+ *   d_G          [n_items, ldg] float32, complete for every item with a non-empty column
+ *   d_targets    int32[n_targets] target item ids
+ *   d_sel_in     optional int32[n_targets * nn]: candidate order to use instead of the built-in
+ *                selection (score desc, ties -> larger item id first)
+ *   d_rng        table from rt_rng_table with >= max_iter * min(nn or n_items, n_items) + 64 entries
+ * Outputs
+ *   d_sel_out    optional int32[n_targets * nn] candidate order used (-1 padded)
+ *   d_out_off    int64[n_targets] offset of each target's result in d_out_rows/d_out_vals
+ *   d_out_cnt    int32[n_targets] number of (row, value) pairs.  nn > 0: exactly min(nn,n_items)
+ *                pairs in pick order, zeros included (slim_elastic.py:153); nn == 0: the non-zero
+ *                coefficients in ascending row (sparse_coef_).
+ *   d_out_rows/d_out_vals capacity out_cap pairs in total; on overflow returns RT_ERR_CAPACITY
+ *                after the kernel has finished (*h_needed = pairs required).
+ *   d_stats      optional int32[n_targets * 4] = n_iter, draws, gap evaluations, live-set size
+ * Synchronises the stream.
+ */
+int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, const int32_t *d_targets,
+                  int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
+                  const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
+                  int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                  int64_t *h_needed, int32_t *d_stats, void *stream);
+
+/*
+ * Assemble / merge the item-similarity matrix W (CSC, n_items x n_items) from solver output,
+ * with the LIL-assignment semantics of slim_elastic.py:273-274, 371-374, 556-557:
+ * for every returned pair (i, v) of target j: v != 0 sets W[i,j] = v, v == 0 deletes W[i,j];
+ * entries of column j that were not returned keep their old (stale) value; other columns are
+ * copied.  d_old_* may be NULL (n_old_items = 0) for a fresh matrix; an old matrix smaller than
+ * n_items is resized (slim_elastic.py:326-327).  rows_sorted != 0 promises that each target's
+ * returned rows are ascending (the nn == 0 solver output).  Output capacity out_cap; *h_nnz
+ * receives the size (RT_ERR_CAPACITY if it does not fit).  Rows within a column are ascending.
+ * Synchronises.
+ */
+int rt_w_merge(int32_t n_items, const int32_t *d_old_ptr, const int32_t *d_old_idx,
+               const float *d_old_val, int32_t n_old_items, const int32_t *d_targets,
+               int32_t n_targets, const int64_t *d_off, const int32_t *d_cnt, const int32_t *d_rows,
+               const float *d_vals, int32_t rows_sorted, int32_t *d_wptr, int32_t *d_widx, float *d_wval,
+               int64_t out_cap, int64_t *h_nnz, void *stream);
+
+/* CSC -> CSR (or back) of a float32 matrix, minor indices ascending; used to give the scoring
+ * kernel W by source item. */
+int rt_transpose(int32_t n_major_in, int32_t n_major_out, const int32_t *d_ptr, const int32_t *d_idx,
+                 const float *d_val, int64_t nnz, int32_t *d_optr, int32_t *d_oidx, float *d_oval,
+                 void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Scoring  (replaces SLIMElastic.recommend / recommend_batch / _dense_topk_indicies /
+ * _sparse_topk_indicies, slim_elastic.py:628-818, and similar_items :820-857)
+ * ---------------------------------------------------------------------------------------- */
+
+#define RT_TOPK_DENSE 0  /* every item eligible (incl. score 0 / negative), slim_elastic.py:743-779 */
+#define RT_TOPK_SPARSE 1 /* only non-zero scores eligible, slim_elastic.py:781-818 */
+
+/*
+ * For each of n_query users: s = X[u, :] . W restricted to item columns [j_begin, j_end)
+ * (the shard this GPU owns; pass 0, n_items for all), interacted items removed when
+ * filter_interacted, top-k by (score desc, item id desc).  W is given by SOURCE item (CSR of W:
+ * row i lists (j, W[i,j]) ascending j).  Outputs int32 ids (-1 padded) and float32 scores
+ * [n_query, k]; d_out_cnt[q] = number of valid entries.  1 <= k <= 128.
+ */
+int rt_slim_recommend(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                      const int32_t *d_users, int32_t n_query, const int32_t *d_wrptr,
+                      const int32_t *d_wridx, const float *d_wrval, int32_t n_items, int32_t j_begin,
+                      int32_t j_end, int32_t k, int32_t filter_interacted, int32_t mode,
+                      int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt, void *stream);
+
+/* Candidate-restricted variant (slim_elastic.py:661-672, 722-739): dense scores of the
+ * n_cand candidate items only, NO interacted filter, order (score desc, candidate position desc).
+ * d_out_pos receives positions into the candidate list. */
+int rt_slim_recommend_candidates(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                                 const int32_t *d_users, int32_t n_query, const int32_t *d_wptr,
+                                 const int32_t *d_widx, const float *d_wval, int32_t n_items,
+                                 const int32_t *d_cand, int32_t n_cand, int32_t k, int32_t *d_out_pos,
+                                 float *d_out_scores, int32_t *d_out_cnt, void *stream);
+
+/* Merge per-shard top-k lists: d_ids/d_scores are [n_shards, n_query, k] (as produced by an
+ * all-gather of rt_slim_recommend outputs); result [n_query, k].  New; no reference analogue. */
+int rt_topk_merge(const int32_t *d_ids, const float *d_scores, int32_t n_shards, int32_t n_query,
+                  int32_t k, int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt, void *stream);
+
+/* similar_items (slim_elastic.py:820-857): column j of W (CSC) minus the diagonal, top-k by
+ * score desc (ties: ascending row).  Outputs [n_query, k]. */
+int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d_wval, int32_t n_items,
+                    const int32_t *d_items, int32_t n_query, int32_t k, int32_t *d_out_ids,
+                    float *d_out_scores, int32_t *d_out_cnt, void *stream);
+
+/* Frees the library-owned device scratch (grow-only arenas reused across calls). */
+void rt_release_scratch(void);
+
+/* Launch counters (how many kernels this library has launched since load / since reset). */
+int64_t rt_launch_count(void);
+void rt_launch_count_reset(void);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTREC_B200_H */

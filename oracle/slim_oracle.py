@@ -37,10 +37,11 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    """Compile slim_oracle.c with gcc (see oracle/Makefile)."""
-    src = os.path.join(_HERE, "slim_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE, "CC=gcc"])
+    """Compile slim_oracle.c + gram_model.c with gcc (see oracle/Makefile)."""
+    srcs = [os.path.join(_HERE, f) for f in ("slim_oracle.c", "gram_model.c", "Makefile")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(f) for f in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
     return _LIB_PATH
 
 
@@ -53,6 +54,8 @@ def lib() -> ctypes.CDLL:
         _lib.so_fit_columns.restype = ctypes.c_int
         _lib.so_feature_scores.restype = ctypes.c_int
         _lib.so_num_threads.restype = ctypes.c_int
+        _lib.gm_gram.restype = ctypes.c_int
+        _lib.gm_fit_columns.restype = ctypes.c_int
     return _lib
 
 
@@ -136,6 +139,46 @@ def fit_columns(X_csc, targets: Sequence[int], nn: Optional[int] = None, sel_in:
         _p(sel_out), ctypes.c_int(cap), _p(out_rows), _p(out_vals), _p(out_cnt), _p(stats))
     if rc != 0:
         raise RuntimeError(f"so_fit_columns failed rc={rc}")
+    cols = [(out_rows[t, :out_cnt[t]].copy(), out_vals[t, :out_cnt[t]].copy()) for t in range(T)]
+    return cols, sel_out, stats
+
+
+def gram_model_gram(X_csc) -> np.ndarray:
+    """Dense fp32 Gram matrix exactly as gram_model.c accumulates it (CPU model of the device path)."""
+    n_users, n_items = X_csc.shape
+    cd, ci, cp = _canon(X_csc, "csc")
+    rd, ri, rp = _canon(sp.csc_matrix((cd, ci, cp), shape=(n_users, n_items)).tocsr(), "csr")
+    G = np.zeros((n_items, n_items), dtype=np.float32)
+    lib().gm_gram(ctypes.c_int(n_users), ctypes.c_int(n_items), _p(cd), _p(ci), _p(cp), _p(rd), _p(ri), _p(rp), _p(G))
+    return G
+
+
+def gram_model_fit_columns(X_csc, targets, nn=None, sel_in=None, alpha=0.1, l1_ratio=0.1, max_iter=100, tol=1e-4,
+                           random_state=43, positive=True, G=None):
+    """CPU model of the device Gram-form replay (oracle/gram_model.c).  Same return shape as
+    :func:`fit_columns`; ``stats[t] = (n_iter, draws, gap_evals, live_size)``."""
+    n_users, n_items = X_csc.shape
+    if G is None:
+        G = gram_model_gram(X_csc)
+    nonneg = bool(X_csc.nnz == 0 or X_csc.data.min() >= 0)
+    targets = np.ascontiguousarray(targets, dtype=np.int32)
+    T = len(targets)
+    nn_c = int(nn) if nn else 0
+    cap = nn_c if nn_c > 0 else n_items
+    out_rows = np.zeros((T, cap), dtype=np.int32)
+    out_vals = np.zeros((T, cap), dtype=np.float32)
+    out_cnt = np.zeros(T, dtype=np.int32)
+    stats = np.zeros((T, 4), dtype=np.int64)
+    sel_out = np.full((T, nn_c), -1, dtype=np.int32) if nn_c > 0 else None
+    if sel_in is not None:
+        sel_in = np.ascontiguousarray(sel_in, dtype=np.int32)
+    rc = lib().gm_fit_columns(
+        ctypes.c_int(n_users), ctypes.c_int(n_items), _p(G), ctypes.c_int(T), _p(targets), ctypes.c_int(nn_c),
+        _p(sel_in), ctypes.c_double(alpha), ctypes.c_double(l1_ratio), ctypes.c_int(max_iter), ctypes.c_double(tol),
+        ctypes.c_uint32(sklearn_seed(random_state)), ctypes.c_int(int(positive)), ctypes.c_int(int(nonneg)),
+        _p(sel_out), ctypes.c_int(cap), _p(out_rows), _p(out_vals), _p(out_cnt), _p(stats))
+    if rc != 0:
+        raise RuntimeError(f"gm_fit_columns failed rc={rc}")
     cols = [(out_rows[t, :out_cnt[t]].copy(), out_vals[t, :out_cnt[t]].copy()) for t in range(T)]
     return cols, sel_out, stats
 

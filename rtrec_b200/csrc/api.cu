@@ -1,0 +1,93 @@
+// api.cu -- library-wide plumbing of librtrec_b200: error string, device info, launch counter.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+
+namespace rt {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static int g_sm_count = -1, g_smem_optin = -1, g_cc_major = -1, g_cc_minor = -1;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static int query_device() {
+    if (g_sm_count > 0) return RT_OK;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("no CUDA device available (librtrec_b200 has no CPU fallback)");
+        return RT_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+        set_error("cudaGetDeviceProperties failed (librtrec_b200 has no CPU fallback)");
+        return RT_ERR_NO_DEVICE;
+    }
+    g_sm_count = p.multiProcessorCount;
+    g_smem_optin = (int)p.sharedMemPerBlockOptin;
+    g_cc_major = p.major;
+    g_cc_minor = p.minor;
+    return RT_OK;
+}
+
+static void *g_scr[SCR_SLOTS] = {nullptr};
+static size_t g_scr_cap[SCR_SLOTS] = {0};
+
+void *scratch(int slot, size_t bytes) {
+    if (slot < 0 || slot >= SCR_SLOTS) return nullptr;
+    if (bytes <= g_scr_cap[slot] && g_scr[slot]) return g_scr[slot];
+    if (g_scr[slot]) {
+        cudaDeviceSynchronize();
+        cudaFree(g_scr[slot]);
+        g_scr[slot] = nullptr;
+        g_scr_cap[slot] = 0;
+    }
+    size_t want = align_up(bytes + bytes / 4 + 4096, 1 << 20);
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = align_up(bytes + 256, 1 << 20);
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            set_error("out of device memory: scratch slot %d needs %zu bytes", slot, bytes);
+            return nullptr;
+        }
+    }
+    g_scr[slot] = p;
+    g_scr_cap[slot] = want;
+    return p;
+}
+
+int sm_count() { return query_device() == RT_OK ? g_sm_count : 148; }
+int smem_optin() { return query_device() == RT_OK ? g_smem_optin : 232448; }
+
+}  // namespace rt
+
+extern "C" int rt_version(void) { return 100; }
+extern "C" const char *rt_last_error(void) { return rt::g_err; }
+extern "C" int rt_device_info(int *sm_count, int *smem_optin_bytes, int *cc_major, int *cc_minor) {
+    int rc = rt::query_device();
+    if (rc) return rc;
+    if (sm_count) *sm_count = rt::g_sm_count;
+    if (smem_optin_bytes) *smem_optin_bytes = rt::g_smem_optin;
+    if (cc_major) *cc_major = rt::g_cc_major;
+    if (cc_minor) *cc_minor = rt::g_cc_minor;
+    return RT_OK;
+}
+extern "C" void rt_release_scratch(void) {
+    cudaDeviceSynchronize();
+    for (int i = 0; i < rt::SCR_SLOTS; ++i) {
+        if (rt::g_scr[i]) cudaFree(rt::g_scr[i]);
+        rt::g_scr[i] = nullptr;
+        rt::g_scr_cap[i] = 0;
+    }
+}
+extern "C" int64_t rt_launch_count(void) { return (int64_t)rt::g_launches.load(); }
+extern "C" void rt_launch_count_reset(void) { rt::g_launches.store(0); }

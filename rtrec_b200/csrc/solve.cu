@@ -1,0 +1,579 @@
+// solve.cu -- K4: batched ElasticNet coordinate descent, one CTA per target item column.
+//
+// Replaces, per target column j (reference: /root/reference/rtrec/models/internal/slim_elastic.py):
+//   FeatureSelectionWrapper.fit  :139-154  (score = X^T y, top-n candidates, solve, scatter coef)
+//   ElasticNet(...).fit          :195-208  -> sklearn 1.9.0 _cd_fast.pyx:653-1005
+//
+// The coordinate SEQUENCE of sklearn is replayed exactly (xorshift32 draws, gap-safe screening,
+// stopping rule) but on the Gram matrix instead of the residual ("Gram-form replay"):
+//     q_c = G[j][c], n2_c = G[c][c], h = G w (incremental), tmp = q_c - h_c + w_c n2_c,
+//     R.R = yy - 2 w.q + w.h, R.y = yy - w.q, XtA_c = q_c - h_c - b w_c.
+// The CPU model of this exact algorithm is oracle/gram_model.c; DESIGN.md section 3 has the
+// derivation and the measured agreement with the residual-form reference.
+//
+// Thread organisation: warp 0 walks the draw sequence 32 draws at a time (a visit whose
+// coefficient does not change is a no-op, so a whole batch of no-ops retires in one step; the
+// first changing visit in the batch is applied and the walk resumes after it).  Vector work
+// (h += d*G[c,:], gap, screening, selection) is spread over the whole CTA.
+#include "block_select.cuh"
+#include "common.cuh"
+
+namespace rt {
+
+struct SolveArgs {
+    const float *G;
+    const float *diag;  // G[i][i] gathered contiguously
+    int64_t ldg;
+    int n_items;
+    const int *targets;
+    int n_targets;
+    int nn;  // 0 = all items
+    int NU;  // universe size
+    const int *sel_in;
+    int *sel_out;
+    double a, b, d_w_tol;
+    int max_iter, positive, nonneg;
+    const uint32_t *rng;
+    int64_t *out_off;
+    int *out_cnt;
+    int *out_rows;
+    float *out_vals;
+    int64_t out_cap;
+    unsigned long long *cursor;  // [0] = append cursor (all-items mode), [1] = next target
+    int *stats;
+    char *scratch;
+    size_t scratch_per_cta;
+    int hot_in_smem;  // per-visit arrays live in dynamic shared memory
+    int use_gs;       // dense live x live Gram block cached in shared memory (nn mode)
+};
+
+struct Misc {
+    SelectScratch sel;
+    double red[4][32];
+    int wtot[2][2][32];
+    int t;
+    // event produced by the draw walker
+    int ev_kind;  // 0 = sweep finished, 1 = coefficient update
+    int ev_slot;
+    double ev_delta, ev_wnew;
+    double w_max, d_w_max;
+    double gap, dual_norm;
+};
+
+__device__ __forceinline__ double block_max_d(double v, Misc *ms) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) ms->red[0][warp] = v;
+    __syncthreads();
+    double r = ms->red[0][0];
+    for (int w = 1; w < nw; ++w) r = fmax(r, ms->red[0][w]);
+    return r;
+}
+
+__device__ __forceinline__ void block_sum4(double &v0, double &v1, double &v2, double &v3, Misc *ms) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+    __syncthreads();
+    if (lane == 0) { ms->red[0][warp] = v0; ms->red[1][warp] = v1; ms->red[2][warp] = v2; ms->red[3][warp] = v3; }
+    __syncthreads();
+    v0 = ms->red[0][0]; v1 = ms->red[1][0]; v2 = ms->red[2][0]; v3 = ms->red[3][0];
+    for (int w = 1; w < nw; ++w) { v0 += ms->red[0][w]; v1 += ms->red[1][w]; v2 += ms->red[2][w]; v3 += ms->red[3][w]; }
+}
+
+__global__ void __launch_bounds__(256) slim_solve_kernel(SolveArgs A) {
+    extern __shared__ __align__(16) char dyn_smem[];
+    __shared__ Misc ms;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = NT >> 5;
+    const int NU = A.NU;
+    const bool nnmode = A.nn > 0;
+    const double a = A.a, b = A.b;
+
+    // ---- carve state ----------------------------------------------------------------------
+    // hot (touched per draw): active[NU] i32, live_slot[NU] i32, w[NU] f64, h[NU] f64, qv[NU] f32, n2[NU] f32
+    // cold: feat[NU] i32, live[NU] i32, excl[NU] u8, xta[NU] f32, list[NU] i32, ckey[NU] u32, cidx[NU] i32
+    char *cold = A.scratch + (size_t)blockIdx.x * A.scratch_per_cta;
+    char *hot = A.hot_in_smem ? dyn_smem : cold;
+    size_t ho = 0;
+    auto take = [&](char *&base, size_t &off, size_t bytes) { char *p = base + off; off += (bytes + 15) & ~(size_t)15; return p; };
+    double *w = (double *)take(hot, ho, sizeof(double) * NU);
+    double *h = (double *)take(hot, ho, sizeof(double) * NU);
+    int *active = (int *)take(hot, ho, sizeof(int) * NU);
+    int *live_slot = (int *)take(hot, ho, sizeof(int) * NU);
+    float *qv = (float *)take(hot, ho, sizeof(float) * NU);
+    float *n2 = (float *)take(hot, ho, sizeof(float) * NU);
+    float *Gs = nullptr;
+    if (A.use_gs) Gs = (float *)take(hot, ho, sizeof(float) * (size_t)NU * NU);
+    size_t co = A.hot_in_smem ? 0 : ho;
+    int *feat = (int *)take(cold, co, sizeof(int) * NU);
+    int *live = (int *)take(cold, co, sizeof(int) * NU);
+    float *xta = (float *)take(cold, co, sizeof(float) * NU);
+    int *list = (int *)take(cold, co, sizeof(int) * NU);
+    uint32_t *ckey = (uint32_t *)take(cold, co, sizeof(uint32_t) * NU);
+    int *cidx = (int *)take(cold, co, sizeof(int) * NU);
+    unsigned char *excl = (unsigned char *)take(cold, co, NU);
+
+    const float *G = A.G;
+    const int64_t ld = A.ldg;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) ms.t = (int)atomicAdd(&A.cursor[1], 1ull);
+        __syncthreads();
+        const int t = ms.t;
+        if (t >= A.n_targets) break;
+        const int j = A.targets[t];
+        const float *gj = G + (size_t)j * ld;
+
+        // ---- universe ------------------------------------------------------------------------
+        if (nnmode) {
+            if (A.sel_in) {
+                for (int k = tid; k < NU; k += NT) feat[k] = A.sel_in[(size_t)t * A.nn + k];
+                __syncthreads();
+            } else {
+                auto key_of = [&](int i) -> uint32_t { return float_key(i == j ? 0.0f : gj[i]); };
+                auto elig = [&](int, uint32_t) -> bool { return true; };
+                block_top_n(A.n_items, NU, key_of, elig, &ms.sel, ckey, cidx, feat, (uint32_t *)nullptr);
+            }
+            if (A.sel_out) {
+                for (int k = tid; k < A.nn; k += NT) A.sel_out[(size_t)t * A.nn + k] = k < NU ? feat[k] : -1;
+            }
+        }
+        auto F = [&](int k) -> int { return nnmode ? feat[k] : k; };
+
+        const double yy = (double)gj[j];
+        const double tol_abs = A.d_w_tol * yy;
+
+        // ---- live set (ordered compaction over the universe) ----------------------------------
+        int m = 0;
+        {
+            int buf = 0;
+            for (int base = 0; base < NU; base += NT, buf ^= 1) {
+                const int k = base + tid;
+                bool is_live = false;
+                float qk = 0.f, nk = 0.f;
+                int f = -1;
+                if (k < NU) {
+                    f = F(k);
+                    if (f != j) { qk = gj[f]; nk = A.diag[f]; }
+                    is_live = nk > 0.f && (!(A.positive && A.nonneg) || (double)qk > a);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, is_live);
+                if (lane == 0) ms.wtot[buf][0][warp] = __popc(bal);
+                __syncthreads();
+                int off = m, tot = 0;
+                for (int ww = 0; ww < nwarps; ++ww) { const int c = ms.wtot[buf][0][ww]; if (ww < warp) off += c; tot += c; }
+                if (k < NU) {
+                    if (is_live) {
+                        const int s = off + __popc(bal & ((1u << lane) - 1u));
+                        live_slot[k] = s; live[s] = k; w[s] = 0.0; h[s] = 0.0; qv[s] = qk; n2[s] = nk;
+                    } else live_slot[k] = -1;
+                }
+                m += tot;
+            }
+            __syncthreads();
+        }
+        if (A.use_gs) {
+            for (int e = tid; e < m * m; e += NT) {
+                const int r = e / m, c = e - r * m;
+                Gs[e] = G[(size_t)F(live[r]) * ld + F(live[c])];
+            }
+            __syncthreads();
+        }
+        // G entry between two live slots
+        auto GL = [&](int sr, int sc) -> double {
+            return A.use_gs ? (double)Gs[sr * m + sc] : (double)G[(size_t)F(live[sr]) * ld + F(live[sc])];
+        };
+
+        int n_active = 0, n_iter = 0, n_gap = 0, draws = 0;
+
+        // ---- duality gap over the whole universe (fills xta) ---------------------------------
+        auto eval_gap = [&]() {
+            double wq = 0, wh = 0, l1 = 0, l2 = 0;
+            for (int s = tid; s < m; s += NT) {
+                const double ws = w[s];
+                wq += ws * (double)qv[s]; wh += ws * h[s]; l1 += fabs(ws); l2 += ws * ws;
+            }
+            block_sum4(wq, wh, l1, l2, &ms);
+            // support list (ordered) for the non-live rows
+            int ns = 0;
+            {
+                int buf = 0;
+                for (int base = 0; base < m; base += NT, buf ^= 1) {
+                    const int s = base + tid;
+                    const bool nz = s < m && w[s] != 0.0;
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (lane == 0) ms.wtot[buf][0][warp] = __popc(bal);
+                    __syncthreads();
+                    int off = ns, tot = 0;
+                    for (int ww = 0; ww < nwarps; ++ww) { const int c = ms.wtot[buf][0][ww]; if (ww < warp) off += c; tot += c; }
+                    if (nz) list[off + __popc(bal & ((1u << lane) - 1u))] = s;
+                    ns += tot;
+                }
+                __syncthreads();
+            }
+            double dn = -INFINITY;
+            for (int k = tid; k < NU; k += NT) {
+                const int s = live_slot[k];
+                double v;
+                if (s >= 0) v = (double)qv[s] - h[s] - b * w[s];
+                else {
+                    const int f = F(k);
+                    if (f == j) v = 0.0;
+                    else {
+                        double hk = 0.0;
+                        for (int e = 0; e < ns; ++e) {
+                            const int sc = list[e];
+                            hk += (double)G[(size_t)F(live[sc]) * ld + f] * w[sc];
+                        }
+                        v = (double)gj[f] - hk;
+                    }
+                }
+                xta[k] = (float)v;
+                const double av = A.positive ? v : fabs(v);
+                dn = fmax(dn, av);
+            }
+            dn = block_max_d(dn, &ms);
+            const double Rn = yy - 2.0 * wq + wh, Ry = yy - wq;
+            const double primal = 0.5 * (Rn + b * l2) + a * l1;
+            const double scale = dn > a ? a / dn : 1.0;
+            const double dualv = -0.5 * scale * scale * (Rn + b * l2) + scale * Ry;
+            if (tid == 0) { ms.gap = primal - dualv; ms.dual_norm = dn; }
+            __syncthreads();
+            ++n_gap;
+        };
+
+        // ---- gap-safe screening; rebuilds active[] in ascending universe order ---------------
+        auto screen = [&](bool first) {
+            const double gap = ms.gap, dn = ms.dual_norm;
+            const double denom = a > dn ? a : dn;
+            const double thr = sqrt(2.0 * gap) / a;
+            int na = 0, nd = 0, buf = 0;
+            for (int base = 0; base < NU; base += NT, buf ^= 1) {
+                const int k = base + tid;
+                bool keep = false, drop = false;
+                if (k < NU) {
+                    const int s = live_slot[k];
+                    const int f = F(k);
+                    const double nk = s >= 0 ? (double)n2[s] : (f == j ? 0.0 : (double)A.diag[f]);
+                    bool consider;
+                    if (first) { consider = nk != 0.0; if (!consider) excl[k] = 1; }
+                    else consider = !excl[k];
+                    if (consider) {
+                        const double theta = (double)xta[k] / denom;
+                        const double dk = (1.0 - fabs(theta)) / sqrt(nk + b);
+                        if (dk <= thr) { keep = true; excl[k] = 0; }
+                        else { excl[k] = 1; drop = (s >= 0 && w[s] != 0.0); }
+                    }
+                }
+                const unsigned bk = __ballot_sync(0xffffffffu, keep);
+                const unsigned bd = __ballot_sync(0xffffffffu, drop);
+                if (lane == 0) { ms.wtot[buf][0][warp] = __popc(bk); ms.wtot[buf][1][warp] = __popc(bd); }
+                __syncthreads();
+                int offk = na, totk = 0, offd = nd, totd = 0;
+                for (int ww = 0; ww < nwarps; ++ww) {
+                    const int c = ms.wtot[buf][0][ww], d = ms.wtot[buf][1][ww];
+                    if (ww < warp) { offk += c; offd += d; }
+                    totk += c; totd += d;
+                }
+                if (keep) active[offk + __popc(bk & ((1u << lane) - 1u))] = k;
+                if (drop) list[offd + __popc(bd & ((1u << lane) - 1u))] = live_slot[k];
+                na += totk; nd += totd;
+            }
+            __syncthreads();
+            // excluded coordinates that still carry weight: remove their contribution from h
+            for (int e = 0; e < nd; ++e) {
+                const int sc = list[e];
+                const double wsc = w[sc];
+                __syncthreads();
+                for (int r = tid; r < m; r += NT) h[r] -= wsc * GL(r, sc);
+                if (tid == 0) w[sc] = 0.0;
+                __syncthreads();
+            }
+            n_active = na;
+        };
+
+        eval_gap();
+        bool done = ms.gap <= tol_abs;
+        if (!done && m == 0) { done = true; n_iter = A.max_iter; }  // nothing can move: w stays 0
+        if (!done) {
+            screen(true);
+            int64_t tdraw = 0;  // index of the next draw in the rng table
+            for (int it = 0; it < A.max_iter; ++it) {
+                // ---------------- one sweep: n_active draws ----------------
+                int v = 0;
+                double wmax_l = 0.0, dwmax_l = 0.0;  // per-lane running maxima (warp 0)
+                for (;;) {
+                    if (warp == 0) {
+                        int kind = 0;
+                        while (v < n_active) {
+                            const int nb = min(32, n_active - v);
+                            bool upd = false;
+                            int s = -1;
+                            double wc = 0.0, wn = 0.0;
+                            if (lane < nb) {
+                                const uint32_t r = A.rng[tdraw + lane];
+                                const int k = active[r % (uint32_t)n_active];
+                                s = live_slot[k];
+                                if (s >= 0) {
+                                    wc = w[s];
+                                    const double nk = (double)n2[s];
+                                    const double tmp = (double)qv[s] - h[s] + wc * nk;
+                                    if (A.positive && tmp < 0.0) wn = 0.0;
+                                    else {
+                                        double mag = fabs(tmp) - a;
+                                        if (!(mag > 0.0)) mag = 0.0;
+                                        wn = (tmp > 0.0 ? mag : (tmp < 0.0 ? -mag : 0.0)) / (nk + b);
+                                    }
+                                    upd = wn != wc;
+                                }
+                            }
+                            const unsigned mask = __ballot_sync(0xffffffffu, upd);
+                            if (mask == 0u) {
+                                wmax_l = fmax(wmax_l, fabs(wn));
+                                v += nb; tdraw += nb;
+                                continue;
+                            }
+                            const int L0 = __ffs(mask) - 1;
+                            if (lane <= L0) wmax_l = fmax(wmax_l, fabs(wn));
+                            if (lane == L0) {
+                                dwmax_l = fmax(dwmax_l, fabs(wn - wc));
+                                ms.ev_slot = s; ms.ev_delta = wn - wc; ms.ev_wnew = wn;
+                            }
+                            v += L0 + 1; tdraw += L0 + 1;
+                            kind = 1;
+                            break;
+                        }
+                        if (lane == 0) ms.ev_kind = kind;
+                        if (kind == 0) {
+                            const double wm = warp_max(wmax_l), dm = warp_max(dwmax_l);
+                            if (lane == 0) { ms.w_max = wm; ms.d_w_max = dm; }
+                        }
+                    }
+                    __syncthreads();
+                    if (ms.ev_kind == 0) break;
+                    {
+                        const int sc = ms.ev_slot;
+                        const double d = ms.ev_delta;
+                        for (int r = tid; r < m; r += NT) h[r] += d * GL(r, sc);
+                        if (tid == 0) w[sc] = ms.ev_wnew;
+                    }
+                    __syncthreads();
+                }
+                draws += n_active;
+                n_iter = it + 1;
+                const double w_max = ms.w_max, d_w_max = ms.d_w_max;
+                if (w_max == 0.0 || d_w_max / w_max <= A.d_w_tol || it == A.max_iter - 1) {
+                    eval_gap();
+                    if (ms.gap <= tol_abs) break;
+                    screen(false);
+                }
+            }
+        }
+
+        // ---- output ---------------------------------------------------------------------------
+        if (A.stats && tid == 0) {
+            A.stats[(size_t)t * 4 + 0] = n_iter; A.stats[(size_t)t * 4 + 1] = draws;
+            A.stats[(size_t)t * 4 + 2] = n_gap; A.stats[(size_t)t * 4 + 3] = m;
+        }
+        if (nnmode) {
+            const int64_t off = (int64_t)t * NU;
+            for (int k = tid; k < NU; k += NT) {
+                const int s = live_slot[k];
+                A.out_rows[off + k] = feat[k];
+                A.out_vals[off + k] = s >= 0 ? (float)w[s] : 0.0f;
+            }
+            if (tid == 0) { A.out_off[t] = off; A.out_cnt[t] = NU; }
+        } else {
+            // non-zero coefficients in ascending row: live slots are already ascending in k
+            int cnt = 0;
+            {
+                int buf = 0;
+                for (int base = 0; base < m; base += NT, buf ^= 1) {
+                    const int s = base + tid;
+                    const bool nz = s < m && (float)w[s] != 0.0f;
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (lane == 0) ms.wtot[buf][0][warp] = __popc(bal);
+                    __syncthreads();
+                    int off = cnt, tot = 0;
+                    for (int ww = 0; ww < nwarps; ++ww) { const int c = ms.wtot[buf][0][ww]; if (ww < warp) off += c; tot += c; }
+                    if (nz) list[off + __popc(bal & ((1u << lane) - 1u))] = s;
+                    cnt += tot;
+                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const unsigned long long o = atomicAdd(&A.cursor[0], (unsigned long long)cnt);
+                A.out_off[t] = (int64_t)o; A.out_cnt[t] = cnt;
+                ms.ev_delta = (double)o;  // broadcast
+            }
+            __syncthreads();
+            const int64_t off = (int64_t)ms.ev_delta;
+            if (off + cnt <= A.out_cap) {
+                for (int e = tid; e < cnt; e += NT) {
+                    const int s = list[e];
+                    A.out_rows[off + e] = live[s];
+                    A.out_vals[off + e] = (float)w[s];
+                }
+            }
+        }
+    }
+}
+
+__global__ void gather_diag_kernel(const float *G, int64_t ld, int n, float *diag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) diag[i] = G[(size_t)i * ld + i];
+}
+
+// ---- xorshift32 table -------------------------------------------------------------------------
+// GF(2) jump-ahead: state after t steps = M^t * state.  Each thread jumps to the start of its
+// 64-draw segment with the precomputed powers M^(2^b) and then iterates.
+__constant__ uint32_t c_xs_pow[40][32];  // column images of M^(2^b), b < 40
+
+__global__ void rng_table_kernel(uint32_t seed, int64_t n, uint32_t *out) {
+    const int64_t seg = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t start = seg * 64;
+    if (start >= n) return;
+    uint32_t s = seed == 0 ? 1u : seed;
+    for (int bit = 0; bit < 40; ++bit) {
+        if ((start >> bit) & 1) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r ^= ((s >> c) & 1u) ? c_xs_pow[bit][c] : 0u;
+            s = r;
+        }
+    }
+    const int64_t end = start + 64 < n ? start + 64 : n;
+    for (int64_t t = start; t < end; ++t) {
+        s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+        out[t] = s & 0x7fffffffu;  // % (RAND_R_MAX + 1)
+    }
+}
+
+static uint32_t xs_step(uint32_t s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
+
+static int upload_xs_powers() {
+    static bool done = false;
+    if (done) return RT_OK;
+    static uint32_t pw[40][32];
+    for (int c = 0; c < 32; ++c) pw[0][c] = xs_step(1u << c);
+    for (int bpow = 1; bpow < 40; ++bpow)
+        for (int c = 0; c < 32; ++c) {
+            // M^(2^b) e_c = M^(2^(b-1)) (M^(2^(b-1)) e_c)
+            uint32_t v = pw[bpow - 1][c], r = 0;
+            for (int k = 0; k < 32; ++k) if ((v >> k) & 1u) r ^= pw[bpow - 1][k];
+            pw[bpow][c] = r;
+        }
+    RT_CUDA(cudaMemcpyToSymbol(c_xs_pow, pw, sizeof(pw)));
+    done = true;
+    return RT_OK;
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" int rt_rng_table(uint32_t seed, int64_t n, uint32_t *d_out, void *stream) {
+    RT_ARG(n >= 0 && (n == 0 || d_out), "rng table output");
+    if (n == 0) return RT_OK;
+    int rc = upload_xs_powers();
+    if (rc) return rc;
+    const int64_t segs = (n + 63) / 64;
+    const int bs = 128;
+    rng_table_kernel<<<(unsigned)((segs + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(seed, n, d_out);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+namespace {
+struct SolvePlan {
+    int NU, NT, grid, hot_in_smem, use_gs;
+    size_t hot_bytes, cold_bytes, smem_bytes, scratch_per_cta;
+};
+
+SolvePlan make_plan(int n_items, int nn, int n_targets) {
+    SolvePlan p;
+    p.NU = nn > 0 ? (nn < n_items ? nn : n_items) : n_items;
+    auto pad = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t NU = (size_t)p.NU;
+    size_t hot = 2 * pad(8 * NU) + 4 * pad(4 * NU);
+    p.use_gs = (nn > 0 && NU <= 160) ? 1 : 0;
+    if (p.use_gs) hot += pad(4 * NU * NU);
+    size_t cold = 6 * pad(4 * NU) + pad(NU);
+    const int optin = rt::smem_optin();
+    const size_t static_smem = sizeof(Misc) + 64;
+    p.hot_in_smem = (hot + static_smem <= (size_t)optin - 1024) ? 1 : 0;
+    p.hot_bytes = hot;
+    p.cold_bytes = cold;
+    p.smem_bytes = p.hot_in_smem ? hot : 0;
+    p.scratch_per_cta = rt::align_up(cold + (p.hot_in_smem ? 0 : hot) + 256, 256);
+    p.NT = nn > 0 ? 64 : 128;
+    // resident CTAs per SM, bounded by shared memory
+    int per_sm = nn > 0 ? 16 : 4;
+    if (p.hot_in_smem) {
+        int fit = (int)(((size_t)optin) / (hot + static_smem + 1024));
+        if (fit < 1) fit = 1;
+        if (fit < per_sm) per_sm = fit;
+    }
+    int grid = rt::sm_count() * per_sm;
+    if (grid > n_targets) grid = n_targets;
+    if (grid < 1) grid = 1;
+    p.grid = grid;
+    return p;
+}
+}  // namespace
+
+extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, const int32_t *d_targets,
+                             int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
+                             const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
+                             int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                             int64_t *h_needed, int32_t *d_stats, void *stream) {
+    RT_ARG(cfg != nullptr, "cfg");
+    RT_ARG(n_items > 0 && ldg >= n_items, "n_items/ldg");
+    RT_ARG(n_targets >= 0, "n_targets");
+    RT_ARG(cfg->nn >= 0, "nn");
+    RT_ARG(cfg->alpha * cfg->l1_ratio > 0.0, "alpha*l1_ratio must be > 0 (L1 penalty; gap-safe screening path)");
+    if (h_needed) *h_needed = 0;
+    if (n_targets == 0) return RT_OK;
+    RT_ARG(d_G && d_targets && d_rng && d_out_off && d_out_cnt && d_out_rows && d_out_vals, "null pointer");
+    SolvePlan p = make_plan(n_items, cfg->nn, n_targets);
+    RT_ARG(rng_len >= (int64_t)cfg->max_iter * p.NU + 64, "rng table too short");
+    const size_t diag_bytes = rt::align_up((size_t)n_items * sizeof(float));
+    void *d_workspace = rt::scratch(SCR_SOLVE, (size_t)p.grid * p.scratch_per_cta + 1024 + diag_bytes);
+    if (!d_workspace) return RT_ERR_CUDA;
+    if (cfg->nn > 0) RT_ARG(out_cap >= (int64_t)n_targets * p.NU, "out_cap < n_targets * nn");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    SolveArgs A;
+    A.G = d_G; A.ldg = ldg; A.n_items = n_items; A.targets = d_targets; A.n_targets = n_targets;
+    A.nn = cfg->nn; A.NU = p.NU; A.sel_in = d_sel_in; A.sel_out = d_sel_out;
+    A.a = (double)(float)(cfg->alpha * cfg->l1_ratio * (double)cfg->n_samples);
+    A.b = (double)(float)(cfg->alpha * (1.0 - cfg->l1_ratio) * (double)cfg->n_samples);
+    A.d_w_tol = (double)(float)cfg->tol;
+    A.max_iter = cfg->max_iter; A.positive = cfg->positive; A.nonneg = cfg->nonneg;
+    A.rng = d_rng; A.out_off = d_out_off; A.out_cnt = d_out_cnt; A.out_rows = d_out_rows;
+    A.out_vals = d_out_vals; A.out_cap = out_cap; A.stats = d_stats;
+    A.cursor = (unsigned long long *)d_workspace;
+    float *d_diag = (float *)((char *)d_workspace + 1024);
+    A.diag = d_diag;
+    A.scratch = (char *)d_workspace + 1024 + diag_bytes;
+    A.scratch_per_cta = p.scratch_per_cta;
+    A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
+    RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
+    gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(d_G, ldg, n_items, d_diag);
+    RT_CHECK_LAUNCH();
+    RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+    slim_solve_kernel<<<p.grid, p.NT, p.smem_bytes, st>>>(A);
+    RT_CHECK_LAUNCH();
+    unsigned long long cur[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(cur, d_workspace, sizeof(cur), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    const int64_t needed = cfg->nn > 0 ? (int64_t)n_targets * p.NU : (int64_t)cur[0];
+    if (h_needed) *h_needed = needed;
+    if (needed > out_cap) {
+        rt::set_error("rt_slim_solve: output capacity %lld < %lld pairs needed", (long long)out_cap, (long long)needed);
+        return RT_ERR_CAPACITY;
+    }
+    return RT_OK;
+}
