@@ -1,0 +1,294 @@
+"""Device-resident containers and thin Python wrappers over the C-ABI (``include/rtrec_b200.h``).
+
+PyTorch is used here only as plumbing: device allocations (``torch.empty``), the current CUDA
+stream and host<->device copies.  Every computation is a call into ``librtrec_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import FitConfig, RtrecB200Error, check
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise RtrecB200Error("no CUDA device visible: rtrec_b200 runs its hot path on the GPU only (no CPU fallback)")
+    _lib.load()
+    return t
+
+
+def dev():
+    t = require_cuda()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def stream_ptr():
+    return C.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def to_dev(a: np.ndarray, dtype=None):
+    t = require_cuda()
+    x = t.from_numpy(np.ascontiguousarray(a if dtype is None else a.astype(dtype, copy=False)))
+    return x.to(dev(), non_blocking=False)
+
+
+def empty(n, dtype):
+    t = require_cuda()
+    return t.empty(int(n), dtype=dtype, device=dev())
+
+
+def zeros(n, dtype):
+    t = require_cuda()
+    return t.zeros(int(n), dtype=dtype, device=dev())
+
+
+# --------------------------------------------------------------------------------------------
+@dataclass
+class DeviceMatrix:
+    """Interaction matrix X on the device in CSR and CSC (plus the COO column ids of the CSC order).
+    float32 values / int32 indices like the reference's scipy matrices (interactions.py:276,303)."""
+    n_users: int
+    n_items: int
+    nnz: int
+    rptr: object
+    ridx: object
+    rval: object
+    cptr: object
+    cidx: object
+    cval: object
+    ccol: object
+    nonneg: bool
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        return self.n_users, self.n_items
+
+    @staticmethod
+    def from_scipy(X) -> "DeviceMatrix":
+        """Upload a host scipy matrix (operator-level API used by tests / HybridSlimFM-style callers)."""
+        import scipy.sparse as sp
+        t = require_cuda()
+        csr = sp.csr_matrix(X, dtype=np.float32)
+        csr.sort_indices()
+        csc = sp.csc_matrix(X, dtype=np.float32)
+        csc.sort_indices()
+        n_users, n_items = csr.shape
+        ccol = np.repeat(np.arange(n_items, dtype=np.int32), np.diff(csc.indptr).astype(np.int64))
+        nonneg = bool(csr.nnz == 0 or csr.data.min() >= 0)
+        return DeviceMatrix(
+            n_users, n_items, int(csr.nnz),
+            to_dev(csr.indptr, np.int32), to_dev(csr.indices, np.int32), to_dev(csr.data, np.float32),
+            to_dev(csc.indptr, np.int32), to_dev(csc.indices, np.int32), to_dev(csc.data, np.float32),
+            to_dev(ccol, np.int32), nonneg)
+
+    def to_scipy_csr(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.rval[:self.nnz].cpu().numpy(), self.ridx[:self.nnz].cpu().numpy(),
+                              self.rptr.cpu().numpy()), shape=self.shape)
+
+    def to_scipy_csc(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.cval[:self.nnz].cpu().numpy(), self.cidx[:self.nnz].cpu().numpy(),
+                              self.cptr.cpu().numpy()), shape=self.shape)
+
+
+@dataclass
+class DeviceW:
+    """Item-similarity matrix W (n_items x n_items) on the device: CSC (by target column, what the
+    reference exposes as ``item_similarity``) and CSR (by source item, what scoring streams)."""
+    n_items: int
+    nnz: int
+    wptr: object
+    widx: object
+    wval: object
+    wrptr: object
+    wridx: object
+    wrval: object
+
+    def to_scipy_csc(self, dtype=np.float32):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.wval[:self.nnz].cpu().numpy().astype(dtype), self.widx[:self.nnz].cpu().numpy(),
+                              self.wptr.cpu().numpy()), shape=(self.n_items, self.n_items))
+
+    @staticmethod
+    def from_scipy(W) -> "DeviceW":
+        import scipy.sparse as sp
+        t = require_cuda()
+        csc = sp.csc_matrix(W, dtype=np.float32)
+        csc.sort_indices()
+        n = csc.shape[1]
+        wptr, widx, wval = to_dev(csc.indptr, np.int32), to_dev(csc.indices, np.int32), to_dev(csc.data, np.float32)
+        return _finish_w(n, int(csc.nnz), wptr, widx, wval)
+
+
+def _finish_w(n_items: int, nnz: int, wptr, widx, wval) -> DeviceW:
+    t = torch()
+    wrptr = empty(n_items + 1, t.int32)
+    wridx = empty(max(nnz, 1), t.int32)
+    wrval = empty(max(nnz, 1), t.float32)
+    check(_lib.load().rt_transpose(n_items, n_items, ptr(wptr), ptr(widx), ptr(wval), nnz, ptr(wrptr), ptr(wridx),
+                                   ptr(wrval), stream_ptr()), "rt_transpose")
+    return DeviceW(n_items, nnz, wptr, widx, wval, wrptr, wridx, wrval)
+
+
+# --------------------------------------------------------------------------------------------
+_rng_cache: Dict[Tuple[int, int], object] = {}
+
+
+def rng_table(seed: int, n: int):
+    """xorshift32 draw table (device); cached per (device, seed) and grown on demand."""
+    t = require_cuda()
+    key = (t.cuda.current_device(), int(seed))
+    cur = _rng_cache.get(key)
+    if cur is not None and cur.numel() >= n:
+        return cur
+    n_alloc = int(n * 1.25) + 1024
+    out = empty(n_alloc, t.int32)
+    check(_lib.load().rt_rng_table(C.c_uint32(seed), n_alloc, ptr(out), stream_ptr()), "rt_rng_table")
+    _rng_cache[key] = out
+    return out
+
+
+def gram(X: DeviceMatrix, e_begin: int = 0, e_end: Optional[int] = None, out=None):
+    """Dense item-item Gram matrix G (n_items x n_items float32) on the device (K3)."""
+    t = require_cuda()
+    I = X.n_items
+    if out is None:
+        out = t.zeros((I, I), dtype=t.float32, device=dev())
+    e_end = X.nnz if e_end is None else e_end
+    check(_lib.load().rt_gram_rows(ptr(X.ccol), ptr(X.cidx), ptr(X.cval), int(e_begin), int(e_end), ptr(X.rptr),
+                                   ptr(X.ridx), ptr(X.rval), ptr(out), I, stream_ptr()), "rt_gram_rows")
+    return out
+
+
+@dataclass
+class SolveResult:
+    targets: object   # int32 device [T]
+    off: object       # int64 device [T]
+    cnt: object       # int32 device [T]
+    rows: object      # int32 device
+    vals: object      # float32 device
+    sel: Optional[object]    # int32 device [T, nn] or None
+    stats: object     # int32 device [T, 4]
+    rows_sorted: bool
+    n_pairs: int
+
+
+def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool = False) -> SolveResult:
+    """Batched ElasticNet solves on the Gram matrix (K4)."""
+    t = require_cuda()
+    lib = _lib.load()
+    T = int(targets.numel())
+    nn = int(cfg.nn)
+    NU = min(nn, n_items) if nn > 0 else n_items
+    rng = rng_table(int(cfg.seed), int(cfg.max_iter) * NU + 64)
+    off = empty(max(T, 1), t.int64)
+    cnt = zeros(max(T, 1), t.int32)
+    stats = zeros(max(T, 1) * 4, t.int32)
+    sel_out = empty(max(T * nn, 1), t.int32) if (nn > 0 and want_sel) else None
+    cap = T * NU if nn > 0 else max(T * min(NU, 256), 1024)
+    needed = C.c_int64(0)
+    while True:
+        rows = empty(max(cap, 1), t.int32)
+        vals = empty(max(cap, 1), t.float32)
+        rc = lib.rt_slim_solve(ptr(G), G.stride(0), n_items, ptr(targets), T, C.byref(cfg), ptr(sel_in), ptr(rng),
+                               rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows), ptr(vals), cap, C.byref(needed),
+                               ptr(stats), stream_ptr())
+        if rc == _lib.RT_ERR_CAPACITY and needed.value > cap:
+            cap = int(needed.value)
+            continue
+        check(rc, "rt_slim_solve")
+        break
+    return SolveResult(targets, off, cnt, rows, vals, sel_out.view(T, nn) if sel_out is not None else None,
+                       stats.view(-1, 4)[:T], nn == 0, int(needed.value))
+
+
+def w_merge(old: Optional[DeviceW], n_items: int, res: SolveResult) -> DeviceW:
+    """Assemble / merge W with the reference's LIL-assignment semantics (K5)."""
+    t = require_cuda()
+    lib = _lib.load()
+    T = int(res.targets.numel())
+    old_nnz = old.nnz if old is not None else 0
+    cap = old_nnz + res.n_pairs + 16
+    wptr = empty(n_items + 1, t.int32)
+    widx = empty(cap, t.int32)
+    wval = empty(cap, t.float32)
+    nnz = C.c_int64(0)
+    check(lib.rt_w_merge(n_items, ptr(old.wptr) if old else None, ptr(old.widx) if old else None,
+                         ptr(old.wval) if old else None, old.n_items if old else 0, ptr(res.targets), T, ptr(res.off),
+                         ptr(res.cnt), ptr(res.rows), ptr(res.vals), 1 if res.rows_sorted else 0, ptr(wptr), ptr(widx),
+                         ptr(wval), cap, C.byref(nnz), stream_ptr()), "rt_w_merge")
+    n = int(nnz.value)
+    return _finish_w(n_items, n, wptr, widx[:max(n, 1)], wval[:max(n, 1)])
+
+
+def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int,
+              j_begin: int = 0, j_end: Optional[int] = None):
+    """Fused scoring + filter + top-k for a batch of users (K6).  Returns device (ids, scores, cnt)."""
+    t = require_cuda()
+    Q = int(users.numel())
+    ids = empty(max(Q * k, 1), t.int32)
+    scores = empty(max(Q * k, 1), t.float32)
+    cnt = empty(max(Q, 1), t.int32)
+    j_end = W.n_items if j_end is None else j_end
+    check(_lib.load().rt_slim_recommend(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr), ptr(W.wridx),
+                                        ptr(W.wrval), W.n_items, int(j_begin), int(j_end), int(k),
+                                        1 if filter_interacted else 0, int(mode), ptr(ids), ptr(scores), ptr(cnt),
+                                        stream_ptr()), "rt_slim_recommend")
+    return ids.view(Q, k) if Q else ids[:0].view(0, k), scores.view(Q, k) if Q else scores[:0].view(0, k), cnt[:Q]
+
+
+def recommend_candidates(X: DeviceMatrix, users, W: DeviceW, cand, k: int):
+    t = require_cuda()
+    Q = int(users.numel())
+    pos = empty(max(Q * k, 1), t.int32)
+    scores = empty(max(Q * k, 1), t.float32)
+    cnt = empty(max(Q, 1), t.int32)
+    check(_lib.load().rt_slim_recommend_candidates(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wptr),
+                                                   ptr(W.widx), ptr(W.wval), W.n_items, ptr(cand), int(cand.numel()),
+                                                   int(k), ptr(pos), ptr(scores), ptr(cnt), stream_ptr()),
+          "rt_slim_recommend_candidates")
+    return pos.view(Q, k), scores.view(Q, k), cnt[:Q]
+
+
+def similar(W: DeviceW, items, k: int):
+    t = require_cuda()
+    Q = int(items.numel())
+    ids = empty(max(Q * k, 1), t.int32)
+    scores = empty(max(Q * k, 1), t.float32)
+    cnt = empty(max(Q, 1), t.int32)
+    check(_lib.load().rt_slim_similar(ptr(W.wptr), ptr(W.widx), ptr(W.wval), W.n_items, ptr(items), Q, int(k), ptr(ids),
+                                      ptr(scores), ptr(cnt), stream_ptr()), "rt_slim_similar")
+    return ids.view(Q, k), scores.view(Q, k), cnt[:Q]
+
+
+def topk_merge(ids, scores, n_shards: int, n_query: int, k: int):
+    t = require_cuda()
+    out_ids = empty(max(n_query * k, 1), t.int32)
+    out_scores = empty(max(n_query * k, 1), t.float32)
+    cnt = empty(max(n_query, 1), t.int32)
+    check(_lib.load().rt_topk_merge(ptr(ids), ptr(scores), n_shards, n_query, k, ptr(out_ids), ptr(out_scores), ptr(cnt),
+                                    stream_ptr()), "rt_topk_merge")
+    return out_ids.view(n_query, k), out_scores.view(n_query, k), cnt[:n_query]

@@ -1,0 +1,250 @@
+"""``SLIMElastic`` -- the SLIM operator, B200-native.
+
+Same constructor config, methods and error behaviour as the reference operator
+(/root/reference/rtrec/models/internal/slim_elastic.py:156-857); the arithmetic runs in the
+hand-written kernels of ``librtrec_b200.so``:
+
+    fit / fit_in_parallel / partial_fit_items  ->  rt_gram_rows (K3) + rt_slim_solve (K4) + rt_w_merge (K5)
+    recommend / recommend_batch                ->  rt_slim_recommend[_candidates] (K6)
+    similar_items                              ->  rt_slim_similar (K8)
+
+Matrices may be passed as scipy CSR/CSC (uploaded once per call, like the reference's operator
+API) or as :class:`rtrec_b200.device.DeviceMatrix` (what ``SLIM`` passes: no host copy).
+There is no CPU path: without a GPU these methods raise ``RtrecB200Error``.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+from numpy import ndarray
+
+from ... import _lib
+from ... import device as D
+from ..._lib import FitConfig, RT_TOPK_DENSE, RT_TOPK_SPARSE
+
+
+def sklearn_seed(random_state) -> int:
+    """What sklearn's Cython solver seeds its xorshift32 with for ``random_state``
+    (``check_random_state(rs).randint(0, RAND_R_MAX)``, _cd_fast.pyx:748)."""
+    if random_state is None or isinstance(random_state, (int, np.integer)):
+        rs = np.random.RandomState(None if random_state is None else int(random_state))
+    else:
+        rs = random_state
+    return int(rs.randint(0, 2**31 - 1))
+
+
+class SLIMElastic:
+    def __init__(self, config: dict = {}):
+        self.optim_name = config.get("optim", "cd")
+        self.eta0 = config.get("eta0", 0.001)
+        self.alpha = config.get("alpha", 0.1)
+        self.l1_ratio = config.get("l1_ratio", 0.1)
+        self.positive_only = config.get("positive_only", True)
+        self.max_iter = config.get("max_iter", 100)
+        self.tol = config.get("tol", 1e-4)
+        self.random_state = config.get("random_state", 43)
+        self.nn_feature_selection = config.get("nn_feature_selection", None)
+        if self.nn_feature_selection is not None:
+            assert int(self.nn_feature_selection) > 0, f"n_neighbors must be a positive integer: {self.nn_feature_selection}"
+        self._W: Optional[D.DeviceW] = None
+        self._W_host: Optional[sp.csc_matrix] = None  # lazy mirror / pending upload
+        self.last_fit_stats: Optional[np.ndarray] = None
+        self.last_fit_sel: Optional[np.ndarray] = None
+        self.keep_fit_details = bool(config.get("keep_fit_details", False))
+
+    # ------------------------------------------------------------------ item_similarity mirror
+    @property
+    def item_similarity(self) -> Optional[sp.csc_matrix]:
+        """scipy CSC view of W (the attribute the reference exposes, slim_elastic.py:193)."""
+        if self._W_host is None and self._W is not None:
+            self._W_host = self._W.to_scipy_csc()
+        return self._W_host
+
+    @item_similarity.setter
+    def item_similarity(self, W: Optional[sp.spmatrix]) -> None:
+        self._W = None
+        self._W_host = None if W is None else sp.csc_matrix(W, dtype=np.float32)
+
+    def _device_W(self) -> Optional[D.DeviceW]:
+        if self._W is None and self._W_host is not None:
+            self._W = D.DeviceW.from_scipy(self._W_host)
+        return self._W
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_W_host"] = self.item_similarity
+        st["_W"] = None
+        return st
+
+    # ------------------------------------------------------------------ helpers
+    def _check_optim(self) -> None:
+        if self.optim_name == "cd":
+            return
+        if self.optim_name == "sgd":
+            raise NotImplementedError("optim='sgd' (SGDRegressor, slim_elastic.py:209-222) is not on the accelerated path")
+        raise ValueError(f"Invalid Optimizer name: {self.optim_name}")
+
+    def _config(self, X: D.DeviceMatrix) -> FitConfig:
+        nn = int(self.nn_feature_selection) if self.nn_feature_selection is not None else 0
+        return FitConfig(alpha=float(self.alpha), l1_ratio=float(self.l1_ratio), tol=float(self.tol),
+                         max_iter=int(self.max_iter), positive=1 if self.positive_only else 0,
+                         seed=sklearn_seed(self.random_state), nn=nn, n_samples=int(X.n_users),
+                         nonneg=1 if X.nonneg else 0)
+
+    @staticmethod
+    def _as_device(interaction_matrix, allow=("csc", "csr"), err="Interaction matrix must be a scipy.sparse.csr_matrix or scipy.sparse.csc_matrix.") -> D.DeviceMatrix:
+        if isinstance(interaction_matrix, D.DeviceMatrix):
+            return interaction_matrix
+        if (("csc" in allow and isinstance(interaction_matrix, sp.csc_matrix))
+                or ("csr" in allow and isinstance(interaction_matrix, sp.csr_matrix))):
+            return D.DeviceMatrix.from_scipy(interaction_matrix)
+        raise ValueError(err)
+
+    def _fit_device(self, X: D.DeviceMatrix, targets: np.ndarray, keep_old: bool, sel_in: Optional[np.ndarray] = None):
+        """gram -> solve -> merge.  ``targets``: item ids (host int array)."""
+        t = D.require_cuda()
+        cfg = self._config(X)
+        n_items = X.n_items
+        tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
+        G = D.gram(X)
+        sel_dev = None
+        if sel_in is not None and cfg.nn > 0:
+            sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))
+        res = D.solve(G, n_items, tg, cfg, sel_in=sel_dev, want_sel=self.keep_fit_details)
+        del G
+        old = self._device_W() if keep_old else None
+        self._W = D.w_merge(old, n_items, res)
+        self._W_host = None
+        if self.keep_fit_details:
+            self.last_fit_stats = res.stats.cpu().numpy()
+            self.last_fit_sel = res.sel.cpu().numpy() if res.sel is not None else None
+        return self
+
+    # ------------------------------------------------------------------ fit API
+    def fit(self, interaction_matrix, parallel: bool = False, progress_bar: bool = False):
+        """All columns (slim_elastic.py:229-281).  ``parallel`` only selects the reference's
+        merge semantics: the serial path starts from an empty W, ``fit_in_parallel`` keeps
+        entries of an existing W that the new solve does not return (:322-327)."""
+        self._check_optim()
+        if isinstance(interaction_matrix, sp.csc_matrix) and parallel:
+            return self.fit_in_parallel(interaction_matrix, progress_bar=progress_bar)
+        if isinstance(interaction_matrix, sp.csr_matrix) and parallel:
+            logging.warning("Multiprocessing is only supported for CSC format. Fitting in single process.")
+        X = self._as_device(interaction_matrix)
+        if isinstance(interaction_matrix, D.DeviceMatrix) and parallel:
+            return self._fit_device(X, np.arange(X.n_items), keep_old=True)
+        return self._fit_device(X, np.arange(X.n_items), keep_old=False)
+
+    def fit_in_parallel(self, interaction_matrix, item_ids: Optional[ndarray] = None, progress_bar: bool = False,
+                        chunk_size: int = 100, num_workers: Optional[int] = None):
+        """slim_elastic.py:283-386; chunk_size / num_workers are accepted and ignored (the GPU
+        solves all requested columns in one batched launch)."""
+        self._check_optim()
+        X = self._as_device(interaction_matrix, allow=("csc",),
+                            err="Interaction matrix must be in CSC format for parallel processing.")
+        if item_ids is None:
+            item_ids = np.arange(X.n_items)
+        return self._fit_device(X, np.asarray(item_ids), keep_old=True)
+
+    def partial_fit(self, interaction_matrix, user_ids: List[int], parallel: bool = False, progress_bar: bool = False):
+        """slim_elastic.py:495-508 (items of the given users are re-solved)."""
+        csr = interaction_matrix if isinstance(interaction_matrix, sp.csr_matrix) else None
+        if csr is None:
+            raise ValueError("Interaction matrix must be a scipy.sparse.csr_matrix.")
+        items = set()
+        for u in user_ids:
+            items.update(csr[u, :].indices.tolist())
+        return self.partial_fit_items(interaction_matrix, list(items), progress_bar)
+
+    def partial_fit_items(self, interaction_matrix, updated_items: List[int], parallel: bool = False,
+                          progress_bar: bool = False, sel_in: Optional[np.ndarray] = None):
+        """slim_elastic.py:510-564: re-solve ``updated_items`` and merge into the existing W."""
+        self._check_optim()
+        X = self._as_device(interaction_matrix)
+        return self._fit_device(X, np.asarray(list(updated_items), dtype=np.int64), keep_old=True, sel_in=sel_in)
+
+    # ------------------------------------------------------------------ scoring API
+    def _require_fitted(self, what: str) -> D.DeviceW:
+        W = self._device_W()
+        if W is None:
+            raise RuntimeError(f"Model must be fitted before calling {what}.")
+        return W
+
+    def recommend(self, user_id: int, interaction_matrix, candidate_item_ids: Optional[List[int]] = None,
+                  top_k: int = 10, filter_interacted: bool = True, dense_output: bool = True, ret_scores: bool = False):
+        """slim_elastic.py:628-672."""
+        self._require_fitted("predict")
+        return self.recommend_batch([user_id], interaction_matrix, candidate_item_ids, top_k, filter_interacted,
+                                    dense_output, ret_scores)[0]
+
+    def recommend_batch(self, user_ids: List[int], interaction_matrix, candidate_item_ids: Optional[List[int]] = None,
+                        top_k: int = 10, filter_interacted: bool = True, dense_output: bool = True,
+                        ret_scores: bool = False):
+        """slim_elastic.py:674-741."""
+        W = self._require_fitted("batch_recommend")
+        if len(user_ids) == 0:
+            return []
+        X = self._as_device(interaction_matrix, allow=("csr",), err="Interaction matrix must be a scipy.sparse.csr_matrix.")
+        ids, scores, cnt = self.recommend_batch_device(np.asarray(user_ids, dtype=np.int64), X, candidate_item_ids,
+                                                       top_k, filter_interacted, dense_output)
+        out = []
+        for r in range(len(user_ids)):
+            c = int(cnt[r])
+            items = ids[r, :c].tolist()
+            if ret_scores:
+                if candidate_item_ids is None and not dense_output and c == 0:
+                    # zip(*[]) in the reference (slim_elastic.py:815)
+                    raise ValueError("not enough values to unpack (expected 2, got 0)")
+                out.append((items, scores[r, :c].astype(np.float32)))
+            else:
+                out.append(items)
+        return out
+
+    def recommend_batch_device(self, user_ids: np.ndarray, X: D.DeviceMatrix, candidate_item_ids=None, top_k: int = 10,
+                               filter_interacted: bool = True, dense_output: bool = True):
+        """Array form: returns host arrays (ids int64 [Q,k] with -1 padding, scores f32 [Q,k], cnt [Q])."""
+        W = self._require_fitted("batch_recommend")
+        n_items = W.n_items
+        if X.n_items != n_items:
+            # the reference multiplies (n_users x I_x) by (I_w x I_w): shapes must agree
+            raise ValueError(f"dimension mismatch: interaction matrix has {X.n_items} items, W has {n_items}")
+        users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
+        k = int(top_k)
+        if candidate_item_ids is not None:
+            cand_host = np.ascontiguousarray(candidate_item_ids, dtype=np.int32)
+            cand = D.to_dev(cand_host)
+            kk = max(1, min(k, len(cand_host), 128))
+            pos, scores, cnt = D.recommend_candidates(X, users, W, cand, kk)
+            pos = pos.cpu().numpy().astype(np.int64)
+            ids = np.where(pos >= 0, cand_host[np.clip(pos, 0, len(cand_host) - 1)], -1)
+            return ids, scores.cpu().numpy(), cnt.cpu().numpy()
+        kk = max(1, min(k, 128))
+        mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
+        ids, scores, cnt = D.recommend(X, users, W, kk, filter_interacted, mode)
+        return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
+
+    def similar_items(self, item_id: int, top_k: int = 10, ret_ndarrays: bool = False):
+        """slim_elastic.py:820-857."""
+        W = self._require_fitted("similar_items")
+        ids, scores, cnt = self.similar_items_batch(np.asarray([item_id]), top_k)
+        c = int(cnt[0])
+        if ret_ndarrays:
+            return ids[0, :c].astype(np.int32), scores[0, :c]
+        return list(zip(ids[0, :c].tolist(), scores[0, :c].tolist()))
+
+    def similar_items_batch(self, item_ids: np.ndarray, top_k: int = 10):
+        W = self._require_fitted("similar_items")
+        items = D.to_dev(np.ascontiguousarray(item_ids, dtype=np.int32))
+        ids, scores, cnt = D.similar(W, items, max(1, int(top_k)))
+        return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
+
+    # ------------------------------------------------------------------ not on the SLIM hot path
+    def predict(self, *a, **k):
+        self._require_fitted("predict")
+        raise NotImplementedError("dense score export (predict*, slim_elastic.py:566-626) is not part of the accelerated path; use recommend*")
+
+    predict_selected = predict
+    predict_all = predict

@@ -1,0 +1,369 @@
+"""Device-resident user-item interaction store behind the reference's ``UserItemInteractions`` API.
+
+Reference: /root/reference/rtrec/utils/interactions.py:14-353 (dict-of-dicts, python loops).  Here
+the truth lives in HBM as three arrays sorted by ``(user << 32 | item)`` (stored rating f64, last
+timestamp f64); events are buffered on the host in arrival order and folded in by the K1 kernels
+(``rt_store_fold``) the next time anything reads the store, and the float32 CSR/CSC matrices are
+produced by the fused decay+cast+build kernels (``rt_store_build``).  Host-side bookkeeping that
+the reference keeps exact (``max_user_id``, ``max_item_id``, ``max_timestamp``, ``all_item_ids``,
+``hot_items``) stays on the host and is updated per event / per batch with identical results.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import time
+from datetime import datetime, timezone
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .. import _lib
+from .. import device as D
+from .lru import LRUFreqSet
+
+_INT32_MAX = 2**31 - 1
+_FLUSH_AT = 1 << 22  # pending events before an automatic fold
+
+
+class UserItemInteractions:
+    def __init__(self, min_value: int = -5, max_value: int = 10, decay_in_days: Optional[int] = None, **kwargs: Any) -> None:
+        n_recent_hot = kwargs.get("n_recent_hot", 100_000)
+        self.hot_items = LRUFreqSet(capacity=n_recent_hot)
+        assert max_value > min_value, f"max_value should be greater than min_value {max_value} > {min_value}"
+        self.min_value = min_value
+        self.max_value = max_value
+        # half-life decay, interactions.py:36-39
+        self.decay_rate = None if decay_in_days is None else 1.0 - (math.log(2) / decay_in_days)
+        self.all_item_ids: set[int] = set()
+        self.max_user_id = 0
+        self.max_item_id = 0
+        self.max_timestamp = 0.0
+        # device state (torch tensors) -- sorted by key
+        self._keys = None
+        self._vals = None
+        self._stamps = None
+        self._n_pairs = 0
+        self._dev_max_ts = 0.0
+        # host state used only to carry a pickled store until a GPU is needed
+        self._host_state: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None
+        # pending events, arrival order
+        self._pend: List[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
+        self._pend_scalar: List[Tuple[int, int, float, float]] = []
+        self._pend_upsert: Optional[bool] = None
+        self._pend_n = 0
+        self._matrix_cache: Dict[Any, D.DeviceMatrix] = {}
+        self.version = 0  # bumped on every ingest; lets callers cache derived device data
+
+    # ------------------------------------------------------------------ decay helpers
+    def get_decay_rate(self) -> Optional[float]:
+        return self.decay_rate
+
+    def set_decay_rate(self, decay_rate: Optional[float]) -> None:
+        self.decay_rate = decay_rate
+        self._matrix_cache.clear()
+
+    def _apply_decay(self, value: float, last_timestamp: float) -> float:
+        if self.decay_rate is None:
+            return value
+        elapsed_days = (self.max_timestamp - last_timestamp) / 86400.0
+        return value * self.decay_rate ** elapsed_days
+
+    # ------------------------------------------------------------------ ingest
+    def _warn_future(self, tstamp: float) -> None:
+        now = time.time()
+        if tstamp > now + 180.0:
+            cur = datetime.fromtimestamp(now, tz=timezone.utc).isoformat() + "Z"
+            ts = datetime.fromtimestamp(tstamp, tz=timezone.utc).isoformat() + "Z"
+            logging.warning(f"Timestamp {ts} is in the future. Current time is {cur}")
+
+    @staticmethod
+    def _check_id(v: int, what: str) -> int:
+        v = int(v)
+        if v < 0 or v > _INT32_MAX:
+            raise ValueError(f"{what} id {v} is outside [0, 2^31): the device store indexes with int32")
+        return v
+
+    def add_interaction(self, user_id: int, item_id: int, tstamp: float, delta: float = 1.0, upsert: bool = False) -> None:
+        """One event (interactions.py:81-119)."""
+        user_id = self._check_id(user_id, "user")
+        item_id = self._check_id(item_id, "item")
+        tstamp = float(tstamp)
+        delta = float(delta)
+        self._warn_future(tstamp)
+        self.max_timestamp = max(self.max_timestamp, tstamp + 1.0)
+        if self._pend_upsert is not None and self._pend_upsert != bool(upsert):
+            self._flush()
+        self._pend_upsert = bool(upsert)
+        self._pend_scalar.append((user_id, item_id, tstamp, delta))
+        self._pend_n += 1
+        self.all_item_ids.add(item_id)
+        if delta > 0:
+            self.hot_items.add(item_id)
+        self.max_user_id = max(self.max_user_id, user_id)
+        self.max_item_id = max(self.max_item_id, item_id)
+        self._touch()
+        if self._pend_n >= _FLUSH_AT:
+            self._flush()
+
+    def add_interactions_batch(self, user_ids, item_ids, tstamps, deltas, upsert: bool = False) -> None:
+        """Vectorised ``add_interaction`` over arrays in arrival order; same end state."""
+        u = np.ascontiguousarray(user_ids, dtype=np.int64)
+        i = np.ascontiguousarray(item_ids, dtype=np.int64)
+        ts = np.ascontiguousarray(tstamps, dtype=np.float64)
+        d = np.ascontiguousarray(deltas, dtype=np.float64)
+        n = len(u)
+        if n == 0:
+            return
+        if not (len(i) == n and len(ts) == n and len(d) == n):
+            raise ValueError("event arrays must have equal length")
+        if u.min() < 0 or i.min() < 0 or u.max() > _INT32_MAX or i.max() > _INT32_MAX:
+            raise ValueError("ids outside [0, 2^31): the device store indexes with int32")
+        self._warn_future(float(ts.max()))
+        self.max_timestamp = max(self.max_timestamp, float(ts.max()) + 1.0)
+        if self._pend_upsert is not None and self._pend_upsert != bool(upsert):
+            self._flush()
+        self._pend_upsert = bool(upsert)
+        self._seal_scalars()
+        self._pend.append((u.astype(np.int32), i.astype(np.int32), ts, d))
+        self._pend_n += n
+        self.all_item_ids.update(np.unique(i).tolist())
+        pos = d > 0
+        self.hot_items.add_batch(i[pos] if not pos.all() else i)
+        self.max_user_id = max(self.max_user_id, int(u.max()))
+        self.max_item_id = max(self.max_item_id, int(i.max()))
+        self._touch()
+        if self._pend_n >= _FLUSH_AT:
+            self._flush()
+
+    def _touch(self) -> None:
+        self.version += 1
+        if self._matrix_cache:
+            self._matrix_cache.clear()
+
+    def _seal_scalars(self) -> None:
+        if self._pend_scalar:
+            a = np.asarray(self._pend_scalar, dtype=np.float64)
+            self._pend.append((a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2].copy(), a[:, 3].copy()))
+            self._pend_scalar = []
+
+    def _ensure_device_state(self) -> None:
+        if self._host_state is not None:
+            k, v, s = self._host_state
+            t = D.require_cuda()
+            self._keys = D.to_dev(k.view(np.int64))
+            self._vals = D.to_dev(v)
+            self._stamps = D.to_dev(s)
+            self._n_pairs = len(k)
+            self._host_state = None
+
+    def _flush(self) -> None:
+        """Fold the pending events into the device store (K1)."""
+        self._seal_scalars()
+        self._ensure_device_state()
+        if not self._pend:
+            return
+        t = D.require_cuda()
+        lib = _lib.load()
+        if len(self._pend) == 1:
+            u, i, ts, d = self._pend[0]
+        else:
+            u = np.concatenate([p[0] for p in self._pend]); i = np.concatenate([p[1] for p in self._pend])
+            ts = np.concatenate([p[2] for p in self._pend]); d = np.concatenate([p[3] for p in self._pend])
+        upsert = bool(self._pend_upsert)
+        self._pend, self._pend_n, self._pend_upsert = [], 0, None
+        n = len(u)
+        du, di, dts, dd = D.to_dev(u), D.to_dev(i), D.to_dev(ts), D.to_dev(d)
+        cap = self._n_pairs + n
+        ok = D.empty(cap, t.int64); ov = D.empty(cap, t.float64); os_ = D.empty(cap, t.float64)
+        n_out, mts, mu, mi = C.c_int64(0), C.c_double(0), C.c_int32(0), C.c_int32(0)
+        rate = self.decay_rate if self.decay_rate is not None else float("nan")
+        # carried-in maxima: the device recomputes the same running values the host tracks
+        _lib.check(lib.rt_store_fold(D.ptr(du), D.ptr(di), D.ptr(dts), D.ptr(dd), n, int(upsert), float(self.min_value),
+                                     float(self.max_value), rate, D.ptr(self._keys), D.ptr(self._vals),
+                                     D.ptr(self._stamps), self._n_pairs, float(self._dev_max_ts), 0, 0, D.ptr(ok),
+                                     D.ptr(ov), D.ptr(os_), cap, C.byref(n_out), C.byref(mts), C.byref(mu),
+                                     C.byref(mi), D.stream_ptr()), "rt_store_fold")
+        self._n_pairs = int(n_out.value)
+        self._keys, self._vals, self._stamps = ok[:self._n_pairs], ov[:self._n_pairs], os_[:self._n_pairs]
+        self._dev_max_ts = float(mts.value)
+
+    # ------------------------------------------------------------------ device matrices
+    def device_matrix(self, select_items: Optional[List[int]] = None) -> D.DeviceMatrix:
+        """float32 CSR + CSC of the store on the device (K2); cached until the next ingest."""
+        self._flush()
+        key = None if select_items is None else tuple(sorted(set(int(x) for x in select_items)))
+        hit = self._matrix_cache.get(key)
+        if hit is not None:
+            return hit
+        t = D.require_cuda()
+        lib = _lib.load()
+        n_users, n_items = self.shape
+        n = self._n_pairs
+        mask = None
+        if key is not None:
+            m = np.zeros(n_items, dtype=np.uint8)
+            sel = np.asarray([x for x in key if 0 <= x < n_items], dtype=np.int64)
+            m[sel] = 1
+            mask = D.to_dev(m)
+        rptr = D.empty(n_users + 1, t.int32); ridx = D.empty(max(n, 1), t.int32); rval = D.empty(max(n, 1), t.float32)
+        cptr = D.empty(n_items + 1, t.int32); cidx = D.empty(max(n, 1), t.int32); cval = D.empty(max(n, 1), t.float32)
+        ccol = D.empty(max(n, 1), t.int32)
+        nnz, nonneg = C.c_int64(0), C.c_int(0)
+        rate = self.decay_rate if self.decay_rate is not None else float("nan")
+        _lib.check(lib.rt_store_build(D.ptr(self._keys), D.ptr(self._vals), D.ptr(self._stamps), n, rate,
+                                      float(self.max_timestamp), n_users, n_items, D.ptr(mask), D.ptr(rptr), D.ptr(ridx),
+                                      D.ptr(rval), D.ptr(cptr), D.ptr(cidx), D.ptr(cval), D.ptr(ccol), C.byref(nnz),
+                                      C.byref(nonneg), D.stream_ptr()), "rt_store_build")
+        X = D.DeviceMatrix(n_users, n_items, int(nnz.value), rptr, ridx, rval, cptr, cidx, cval, ccol, bool(nonneg.value))
+        self._matrix_cache[key] = X
+        return X
+
+    # ------------------------------------------------------------------ point queries
+    def _lookup(self, user_id: int, item_id: int) -> Optional[Tuple[float, float]]:
+        self._flush()
+        if self._n_pairs == 0 or user_id < 0 or item_id < 0:
+            return None
+        t = D.require_cuda()
+        q = D.to_dev(np.array([(int(user_id) << 32) | int(item_id)], dtype=np.int64))
+        v = D.empty(1, t.float64); s = D.empty(1, t.float64); f = D.empty(1, t.uint8)
+        _lib.check(_lib.load().rt_store_lookup(D.ptr(self._keys), D.ptr(self._vals), D.ptr(self._stamps), self._n_pairs,
+                                               D.ptr(q), 1, D.ptr(v), D.ptr(s), D.ptr(f), D.stream_ptr()),
+                   "rt_store_lookup")
+        if int(f.item()) == 0:
+            return None
+        return float(v.item()), float(s.item())
+
+    def has_interaction(self, user_id: int, item_id: int) -> bool:
+        return self._lookup(user_id, item_id) is not None
+
+    def get_user_item_rating(self, user_id: int, item_id: int, default_rating: float = 0.0) -> float:
+        found = self._lookup(user_id, item_id)
+        current, last_ts = found if found is not None else (default_rating, 0.0)
+        if current == default_rating:
+            return default_rating
+        return self._apply_decay(current, last_ts)
+
+    def _user_slice(self, user_id: int):
+        """(items int64, vals, stamps) numpy arrays of one user's pairs, ascending item id."""
+        self._flush()
+        if self._n_pairs == 0 or user_id < 0:
+            z = np.zeros(0)
+            return z.astype(np.int64), z, z
+        t = D.require_cuda()
+        bounds = t.tensor([int(user_id) << 32, (int(user_id) + 1) << 32], dtype=t.int64, device=self._keys.device)
+        lo, hi = t.searchsorted(self._keys, bounds).tolist()
+        k = self._keys[lo:hi].cpu().numpy()
+        return k & 0xFFFFFFFF, self._vals[lo:hi].cpu().numpy(), self._stamps[lo:hi].cpu().numpy()
+
+    def get_user_items(self, user_id: int, n_recent: Optional[int] = None) -> List[int]:
+        items, _, stamps = self._user_slice(user_id)
+        if len(items) == 0:
+            return []
+        if n_recent is not None and self._n_users_seen() > n_recent:  # condition kept as in interactions.py:168
+            order = np.argsort(-stamps, kind="stable")
+            return items[order][:n_recent].tolist()
+        return items.tolist()
+
+    def _n_users_seen(self) -> int:
+        return len(self.get_all_users())
+
+    def get_all_item_ids(self) -> List[int]:
+        return list(self.all_item_ids)
+
+    def get_all_users(self) -> List[int]:
+        self._flush()
+        if self._n_pairs == 0:
+            return []
+        t = D.require_cuda()
+        return t.unique(self._keys >> 32).cpu().tolist()
+
+    def get_all_non_interacted_items(self, user_id: int) -> List[int]:
+        interacted = self.get_user_items(user_id)
+        if len(interacted) == 0:
+            return list(self.all_item_ids)
+        return list(self.all_item_ids.difference(interacted))
+
+    def get_all_non_negative_items(self, user_id: int) -> List[int]:
+        items, vals, stamps = self._user_slice(user_id)
+        rated = {int(i): self._apply_decay(float(v), float(s)) if v != 0.0 else 0.0
+                 for i, v, s in zip(items, vals, stamps)}
+        return [i for i in self.all_item_ids if rated.get(i, 0.0) >= 0.0]
+
+    def get_hot_items(self, n: Optional[int] = None, user_id: Optional[int] = None, filter_interacted: bool = True) -> List[int]:
+        interacted: List[int] = []
+        if filter_interacted:
+            assert user_id is not None, "User ID must be provided to filter interacted items."
+            interacted = self.get_user_items(user_id)
+        return list(self.hot_items.get_freq_items(n, exclude_items=interacted))
+
+    def get_users_by_items(self, item_ids: List[int]) -> List[int]:
+        if not item_ids:
+            return []
+        X = self.device_matrix()
+        t = D.torch()
+        cptr = X.cptr.cpu().numpy()
+        parts = []
+        for it in set(int(x) for x in item_ids):
+            if 0 <= it < X.n_items and cptr[it + 1] > cptr[it]:
+                parts.append(X.cidx[int(cptr[it]):int(cptr[it + 1])])
+        if not parts:
+            return []
+        return t.unique(t.cat(parts)).cpu().tolist()
+
+    # ------------------------------------------------------------------ host mirrors (scipy)
+    def to_csr(self, select_users: Optional[List[int]] = None, include_weights: bool = True):
+        import scipy.sparse as sp
+        M = self.device_matrix().to_scipy_csr()
+        if select_users:
+            # the reference appends a user's row once per occurrence and scipy sums duplicates
+            # (interactions.py:264-276), so a user listed m times gets m-fold weights
+            uniq, counts = np.unique(np.asarray(select_users, dtype=np.int64), return_counts=True)
+            ok = (uniq >= 0) & (uniq < M.shape[0])
+            mult = np.zeros(M.shape[0], dtype=np.float32)
+            mult[uniq[ok]] = counts[ok]
+            rows = np.repeat(np.arange(M.shape[0]), np.diff(M.indptr))
+            sel = mult[rows] > 0
+            M = sp.csr_matrix((M.data[sel] * mult[rows[sel]], (rows[sel], M.indices[sel])), shape=M.shape,
+                              dtype=np.float32)
+        if not include_weights:
+            return sp.csr_matrix((np.ones(M.nnz, dtype="int32"), M.indices, M.indptr), shape=M.shape)
+        return M
+
+    def to_csc(self, select_items: Optional[List[int]] = None):
+        return self.device_matrix(select_items).to_scipy_csc()
+
+    def to_coo(self, select_users: Optional[List[int]] = None, select_items: Optional[List[int]] = None):
+        import scipy.sparse as sp
+        M = sp.coo_matrix(self.device_matrix(select_items).to_scipy_csr())
+        if select_users is not None:
+            keep = np.isin(M.row, np.asarray(list(select_users), dtype=np.int64))
+            M = sp.coo_matrix((M.data[keep], (M.row[keep], M.col[keep])), shape=M.shape, dtype=np.float32)
+        return M
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self.max_user_id + 1, self.max_item_id + 1
+
+    # ------------------------------------------------------------------ pickling
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        if self._pend or self._pend_scalar:
+            self._flush()
+            st = dict(self.__dict__)
+        if self._keys is not None:
+            st["_host_state"] = (self._keys.cpu().numpy().view(np.uint64).copy(), self._vals.cpu().numpy().copy(),
+                                 self._stamps.cpu().numpy().copy())
+        for k in ("_keys", "_vals", "_stamps"):
+            st[k] = None
+        st["_n_pairs_host"] = self._n_pairs
+        st["_matrix_cache"] = {}
+        st["_pend"], st["_pend_scalar"], st["_pend_n"], st["_pend_upsert"] = [], [], 0, None
+        return st
+
+    def __setstate__(self, st):
+        st.pop("_n_pairs_host", None)
+        self.__dict__.update(st)
+        if self._host_state is not None:
+            self._n_pairs = len(self._host_state[0])

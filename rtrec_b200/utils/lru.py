@@ -1,0 +1,87 @@
+"""Recency-ordered frequency set used for cold-start "hot items".
+
+Behavioural mirror of the reference's ``LRUFreqSet`` (/root/reference/rtrec/utils/lru.py:11-123):
+keys are kept in least-recently-used -> most-recently-used order with a hit counter; when the set
+is full the least recently used key is evicted; ``get_freq_items`` lists keys by counter
+(descending, ties in recency order).  ``add_batch`` is the vectorised equivalent of calling
+``add`` for every element of an array in order (used by the batched ingest path); it must and does
+produce exactly the same state.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from collections.abc import MutableSet
+from typing import Any, Iterator, List, Optional
+
+import numpy as np
+
+
+class LRUFreqSet(MutableSet):
+    def __init__(self, capacity: int):
+        if capacity <= 0:
+            raise ValueError("Capacity must be greater than 0.")
+        self.capacity = capacity
+        self.data: "OrderedDict[Any, int]" = OrderedDict()
+
+    # -- MutableSet protocol -----------------------------------------------------------------
+    def add(self, value: Any) -> None:
+        hits = self.data.pop(value, None)
+        if hits is None:
+            if len(self.data) >= self.capacity:
+                self.data.popitem(last=False)
+            hits = 0
+        self.data[value] = hits + 1
+
+    def discard(self, value: Any) -> None:
+        if value not in self.data:
+            raise KeyError(value)
+        del self.data[value]
+
+    def __contains__(self, key: Any) -> bool:
+        return key in self.data
+
+    def __iter__(self) -> Iterator[Any]:
+        return iter(self.data)
+
+    def __len__(self) -> int:
+        return len(self.data)
+
+    def __repr__(self) -> str:
+        return f"LRUFreqSet(capacity={self.capacity}, size={len(self.data)})"
+
+    # -- batched update ----------------------------------------------------------------------
+    def add_batch(self, values: np.ndarray) -> None:
+        """Same end state as ``for v in values: self.add(v)``."""
+        n = len(values)
+        if n == 0:
+            return
+        values = np.asarray(values)
+        uniq, inv, counts = np.unique(values, return_inverse=True, return_counts=True)
+        n_fresh = sum(1 for k in uniq.tolist() if k not in self.data)
+        if len(self.data) + n_fresh > self.capacity:
+            # an eviction can happen somewhere inside the batch: replay it event by event
+            for v in values.tolist():
+                self.add(v)
+            return
+        # no eviction: counters add up, touched keys move to the MRU end ordered by last touch
+        last = np.full(len(uniq), -1, dtype=np.int64)
+        last[inv] = np.arange(n)  # later occurrences overwrite earlier ones
+        for j in np.argsort(last, kind="stable").tolist():
+            key = uniq[j].item()
+            self.data[key] = self.data.pop(key, 0) + int(counts[j])
+
+    # -- queries -----------------------------------------------------------------------------
+    def get_freq_items(self, n: Optional[int] = None, exclude_items: List[Any] = []) -> Iterator[Any]:
+        ranked = sorted(self.data.items(), key=lambda kv: kv[1], reverse=True)  # stable: recency breaks ties
+        if len(exclude_items) > 0:
+            emitted = 0
+            for key, _ in ranked:
+                if key in exclude_items:
+                    continue
+                if n is not None and emitted >= n:
+                    break
+                yield key
+                emitted += 1
+        else:
+            for key, _ in (ranked if n is None else ranked[:n]):
+                yield key

@@ -1,0 +1,71 @@
+"""Comparators shared by the parity tests (SURVEY.md 8c rules 4-6)."""
+import numpy as np
+import scipy.sparse as sp
+
+W_TOL = 1e-4        # north_star: W within 1e-4 relative (to the column's largest coefficient)
+W_TOL_FLIP = 1e-3   # columns where a stop/screen decision flipped by one sweep (DESIGN.md "parity")
+
+
+def csc_from(z, prefix, shape=None):
+    if shape is None:
+        shape = tuple(int(x) for x in z[prefix + "_shape"])
+    return sp.csc_matrix((z[prefix + "_data"], z[prefix + "_indices"], z[prefix + "_indptr"]), shape=shape)
+
+
+def w_from(z, prefix):
+    n = len(z[prefix + "_indptr"]) - 1
+    return sp.csc_matrix((z[prefix + "_data"], z[prefix + "_indices"], z[prefix + "_indptr"]), shape=(n, n))
+
+
+def column_errors(W_a, W_b, cols=None):
+    """per column: max|a-b| / max|b| (b = reference), and the number of support mismatches that matter"""
+    A = sp.csc_matrix(W_a, dtype=np.float64)
+    B = sp.csc_matrix(W_b, dtype=np.float64)
+    assert A.shape == B.shape, (A.shape, B.shape)
+    Dm = (A - B).tocsc()
+    n = A.shape[1]
+    cols = range(n) if cols is None else cols
+    rel = np.zeros(n)
+    for j in cols:
+        d = Dm.data[Dm.indptr[j]:Dm.indptr[j + 1]]
+        b = B.data[B.indptr[j]:B.indptr[j + 1]]
+        a = A.data[A.indptr[j]:A.indptr[j + 1]]
+        scale = max(np.abs(b).max() if len(b) else 0.0, np.abs(a).max() if len(a) else 0.0)
+        if len(d):
+            rel[j] = np.abs(d).max() / scale if scale > 0 else np.abs(d).max()
+    return rel
+
+
+def assert_w_parity(W_a, W_b, cols=None, max_flip_frac=0.02, what="W"):
+    rel = column_errors(W_a, W_b, cols)
+    n = len(list(cols)) if cols is not None else W_b.shape[1]
+    bad = int((rel > W_TOL).sum())
+    worst = float(rel.max()) if len(rel) else 0.0
+    assert worst <= W_TOL_FLIP, f"{what}: worst column error {worst:.3e} > {W_TOL_FLIP}"
+    assert bad <= max(1, int(max_flip_frac * n)), f"{what}: {bad}/{n} columns above {W_TOL} (worst {worst:.3e})"
+    return rel
+
+
+def topk_consistent(ids, scores_row, k, eligible_mask, tol=1e-5):
+    """ids is a valid top-k of scores_row over eligible items, up to score ties within tol."""
+    elig = np.flatnonzero(eligible_mask)
+    want = min(k, len(elig))
+    ids = [i for i in ids if i >= 0]
+    if len(ids) != want:
+        return False, f"length {len(ids)} != {want}"
+    if len(set(ids)) != len(ids):
+        return False, "duplicates"
+    if want == 0:
+        return True, ""
+    s = scores_row[elig]
+    kth = np.sort(s)[::-1][want - 1]
+    scale = max(1.0, float(np.abs(s).max()))
+    for i in ids:
+        if not eligible_mask[i]:
+            return False, f"item {i} not eligible"
+        if scores_row[i] < kth - tol * scale:
+            return False, f"item {i} score {scores_row[i]} below kth {kth}"
+    got = scores_row[ids]
+    if np.any(np.diff(got) > tol * scale):
+        return False, "not sorted by score"
+    return True, ""

@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the golden vectors.
+
+Bars (BASELINE.json north_star 6): indices / bookkeeping / store matrices bit-exact; W within 1e-4
+of the column's largest coefficient (columns whose stop decision flips by one sweep: 1e-3, at most
+2 % of columns); top-k lists equal up to score ties.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import slim_oracle as so
+from oracle.synth import synth_events
+from tests.helpers import assert_w_parity, csc_from, topk_consistent, w_from
+
+pytestmark = pytest.mark.gpu
+
+FIT_CASES = [
+    ("slim_all_int", {}),
+    ("slim_nn20_int", {"nn_feature_selection": 20}),
+    ("slim_nn20_cont", {"nn_feature_selection": 20}),
+    ("slim_nn20_decay", {"nn_feature_selection": 20}),
+    ("slim_all_decay_partial", {}),
+    ("slim_nn20_partial", {"nn_feature_selection": 20}),
+    ("slim_all_strids_fit", {}),
+]
+
+
+def _exact(A, B):
+    A = sp.csc_matrix(A); B = sp.csc_matrix(B)
+    A.sort_indices(); B.sort_indices()
+    return (A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+            and np.array_equal(A.data, B.data))
+
+
+# ------------------------------------------------------------------------------------------ store
+@pytest.mark.parametrize("k", range(4))
+def test_store_matches_reference_bit_exact(golden, k):
+    from rtrec_b200.utils.interactions import UserItemInteractions
+    z = golden(f"store_{k}")
+    ev = z["events"]
+    decay = None if z["decay"] < 0 else int(z["decay"])
+    ups = bool(z["upsert"])
+    st = UserItemInteractions(min_value=-5, max_value=10, decay_in_days=decay)
+    u, i = ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64)
+    for a, b in ((0, 1500), (1500, 1501), (1501, 2600)):
+        st.add_interactions_batch(u[a:b], i[a:b], ev[a:b, 2], ev[a:b, 3], upsert=ups)
+        st.device_matrix()  # force a fold per chunk: state must carry over
+    for r in range(2600, len(u)):  # the scalar API interleaves with the batched one
+        st.add_interaction(int(u[r]), int(i[r]), float(ev[r, 2]), float(ev[r, 3]), upsert=ups)
+    X = st.to_csc()
+    ref = sp.csc_matrix((z["X_data"], z["X_indices"], z["X_indptr"]), shape=tuple(z["X_shape"]))
+    assert _exact(X, ref)
+    assert st.max_timestamp == float(z["max_timestamp"])
+    assert (st.max_user_id, st.max_item_id) == (int(z["max_user_id"]), int(z["max_item_id"]))
+    Xs = st.to_csc(z["sel_items"].tolist())
+    refs = sp.csc_matrix((z["Xs_data"], z["Xs_indices"], z["Xs_indptr"]), shape=tuple(z["X_shape"]))
+    assert _exact(Xs, refs)
+    R = sp.csr_matrix(st.to_csr(z["sel_users"].tolist()))
+    refr = sp.csr_matrix((z["R_data"], z["R_indices"], z["R_indptr"]), shape=tuple(z["X_shape"]))
+    assert _exact(R.tocsc(), refr.tocsc())
+    assert list(st.hot_items.get_freq_items(20)) == z["hot_items"].tolist()
+    # CSR and CSC on the device describe the same matrix
+    dm = st.device_matrix()
+    assert _exact(dm.to_scipy_csr().tocsc(), dm.to_scipy_csc())
+
+
+def test_store_edge_cases():
+    from rtrec_b200.utils.interactions import UserItemInteractions
+    st = UserItemInteractions()
+    assert st.to_csc().shape == (1, 1) and st.to_csc().nnz == 0
+    st.add_interaction(1, 10, 1000.0, 5.0)
+    st.add_interaction(1, 10, 1000.0, -5.0)
+    assert st.get_user_item_rating(1, 10) == 0.0           # tests/utils/test_interactions.py:31-36
+    assert 10 in st.get_user_items(1)
+    assert st.to_csc().nnz == 1                              # explicit zero stays
+    st.add_interaction(1, 10, 1001.0, 30.0)
+    assert st.get_user_item_rating(1, 10) == 10.0           # clipped at max_value
+    st.add_interaction(2, 3, 1002.0, 7.0, upsert=True)
+    st.add_interaction(2, 3, 1003.0, 70.0, upsert=True)
+    assert st.get_user_item_rating(2, 3) == 70.0            # upsert is not clipped
+    assert set(st.get_users_by_items([10])) == {1}
+    assert st.get_users_by_items([99]) == []
+
+
+# ------------------------------------------------------------------------------------------ gram
+def test_gram_rows_exact_on_integer_ratings():
+    from rtrec_b200 import device as D
+    U, I, N = 3000, 700, 150000
+    u, i, ts, r = synth_events(U, I, N, seed=3, rating="int")
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    G_ref = so.gram_model_gram(X)
+    G = D.gram(D.DeviceMatrix.from_scipy(X)).cpu().numpy()
+    assert np.array_equal(G, G_ref)
+    assert np.array_equal(G, G.T)
+
+
+# ------------------------------------------------------------------------------------------ fit
+@pytest.mark.parametrize("name,cfg", FIT_CASES)
+def test_fit_matches_reference_golden(golden, name, cfg):
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    z = golden(name)
+    X0 = csc_from(z, "X0")
+    op = SLIMElastic(dict(cfg, keep_fit_details=True))
+    sel0 = z["sel0"] if "sel0" in z else None
+    items0 = z["fit_items0"] if "fit_items0" in z else np.arange(X0.shape[1])
+    op._fit_device(op._as_device(X0), items0, keep_old=False, sel_in=sel0)
+    assert_w_parity(op.item_similarity, w_from(z, "W0"), what=name + " W0")
+    if "W1_data" in z:
+        X1 = csc_from(z, "X1")
+        op.partial_fit_items(X1, z["fit_items1"].tolist(), sel_in=z["sel1"] if "sel1" in z else None)
+        assert_w_parity(op.item_similarity, w_from(z, "W1"), what=name + " W1")
+        # stale entries: columns that were not re-solved are bit-identical to the old matrix
+        W0, W1 = w_from(z, "W0"), op.item_similarity
+        untouched = np.setdiff1d(np.arange(W0.shape[1]), z["fit_items1"])
+        for j in untouched[:50]:
+            assert np.array_equal(W1[:, j].toarray()[:W0.shape[0]], W0[:, j].toarray())
+
+
+@pytest.mark.parametrize("name", ["slim_nn20_int", "slim_nn20_cont", "slim_nn20_decay"])
+def test_candidate_selection_rule(golden, name):
+    """Built-in selection = score desc, ties -> larger item id; equals the reference's picks whenever
+    no tie crosses the cut (continuous ratings), and is a valid top-n otherwise."""
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    z = golden(name)
+    X0 = csc_from(z, "X0")
+    op = SLIMElastic({"nn_feature_selection": 20, "keep_fit_details": True})
+    op.fit(X0)
+    sel = op.last_fit_sel
+    _, sel_or, _ = so.fit_columns(X0, np.arange(X0.shape[1]), 20)
+    assert np.array_equal(sel, sel_or), "device picks differ from the oracle's deterministic rule"
+    if name != "slim_nn20_int":
+        assert np.array_equal(sel, z["sel0"]), "tie-free data: picks must equal the reference's"
+    o = so.SlimOracle({"nn_feature_selection": 20})
+    o.fit(X0, sel_in=sel)
+    assert_w_parity(op.item_similarity, o.item_similarity, what=name)
+
+
+@pytest.mark.parametrize("rating,nn,ncols", [("int", 50, 400), ("cont", 50, 400), ("int", None, 60)])
+def test_fit_ml1m_shape_sampled_columns(rating, nn, ncols):
+    """ML-1M shape (BASELINE configs[0]); oracle on a column sample via partial_fit_items semantics."""
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    U, I, N = 6040, 3706, 1_000_000
+    u, i, ts, r = synth_events(U, I, N, seed=0, rating=rating)
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    rng = np.random.default_rng(1)
+    tg = np.sort(rng.choice(I, ncols, replace=False)).astype(np.int32)
+    op = SLIMElastic({"nn_feature_selection": nn, "keep_fit_details": True})
+    op.partial_fit_items(X, tg.tolist())
+    sel = op.last_fit_sel
+    o = so.SlimOracle({"nn_feature_selection": nn, "n_threads": 8})
+    o.partial_fit_items(X, tg, sel_in=sel)
+    assert_w_parity(op.item_similarity, o.item_similarity, cols=tg, what=f"ml1m {rating} nn={nn}")
+
+
+# ------------------------------------------------------------------------------------------ scoring
+@pytest.mark.parametrize("name", ["slim_all_int", "slim_nn20_cont", "slim_nn20_decay"])
+@pytest.mark.parametrize("dense", [True, False])
+def test_recommend_topk(golden, name, dense):
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    z = golden(name)
+    S = z["scores_dense"]
+    W = w_from(z, "W1") if "W1_data" in z else w_from(z, "W0")
+    n_items = W.shape[0]
+    # rebuild the final X (all events) with the store oracle
+    ev = z["events"]
+    decay = 180 if "decay" in name else None
+    st = so.fold_events(ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 2], ev[:, 3], decay_in_days=decay)
+    X = so.state_to_matrix(st, decay_in_days=decay, fmt="csr")
+    assert X.shape[1] == n_items
+    op = SLIMElastic({})
+    op.item_similarity = W
+    users = z["rec_users"]
+    for filt in (True, False):
+        res = op.recommend_batch(users.tolist(), X, top_k=10, filter_interacted=filt, dense_output=dense, ret_scores=False)
+        for r, uid in enumerate(users):
+            row = X[uid]
+            elig = np.ones(n_items, bool)
+            if filt:
+                elig[row.indices] = False
+            if not dense:
+                elig &= S[uid] != 0
+            ok, why = topk_consistent(res[r], S[uid], 10, elig)
+            assert ok, (name, dense, filt, int(uid), why)
+    # the reference's own lists (filter on): same items wherever scores are separated
+    if z["pass_through"] == (not dense):
+        res = op.recommend_batch(users.tolist(), X, top_k=10, filter_interacted=True, dense_output=dense)
+        same = sum(1 for r in range(len(users)) if res[r] == [x for x in z["rec_top10"][r] if x >= 0])
+        assert same >= 0.9 * len(users), (same, len(users))
+
+
+def test_recommend_candidates_and_errors(golden):
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    z = golden("slim_nn20_cont")
+    W = w_from(z, "W0")
+    ev = z["events"]
+    X = so.state_to_matrix(so.fold_events(ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 2], ev[:, 3]), fmt="csr")
+    op = SLIMElastic({})
+    with pytest.raises(RuntimeError):
+        op.recommend_batch([0], X)
+    with pytest.raises(RuntimeError):
+        op.similar_items(0)
+    op.item_similarity = W
+    cand = [5, 3, 40, 41, 7, 100, 2]
+    o = so.SlimOracle({})
+    o.item_similarity = W
+    users = z["rec_users"][:64].tolist()
+    got = op.recommend_batch(users, X, candidate_item_ids=cand, top_k=3, ret_scores=True)
+    exp = o.recommend_batch(users, X, candidate_item_ids=cand, top_k=3, ret_scores=True)
+    for (gi, gs), (ei, es) in zip(got, exp):
+        assert np.allclose(gs, es, rtol=1e-5, atol=1e-6)
+        assert gi == ei or np.isclose(np.sort(gs), np.sort(es)).all()
+    with pytest.raises(ValueError):
+        op.fit(np.zeros((3, 3)))
+    assert op.recommend_batch([], X) == []
+
+
+def test_similar_items_matches_reference(golden):
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    for name in ("slim_all_int", "slim_nn20_cont"):
+        z = golden(name)
+        W = w_from(z, "W0")
+        op = SLIMElastic({})
+        op.item_similarity = W
+        ids, scores, cnt = op.similar_items_batch(np.arange(W.shape[0]), 10)
+        for j in range(W.shape[0]):
+            c = int(cnt[j])
+            ref_ids = [x for x in z["sim_ids"][j] if x >= 0]
+            assert c == len(ref_ids)
+            assert np.array_equal(scores[j, :c], z["sim_scores"][j, :c])   # same score sequence
+            if len(set(z["sim_scores"][j, :c].tolist())) == c:
+                assert ids[j, :c].tolist() == ref_ids
+
+
+def test_shard_merge_equals_single_pass(golden):
+    from rtrec_b200 import device as D
+    from rtrec_b200._lib import RT_TOPK_DENSE, RT_TOPK_SPARSE
+    z = golden("slim_nn20_cont")
+    W = D.DeviceW.from_scipy(w_from(z, "W0"))
+    ev = z["events"]
+    X = D.DeviceMatrix.from_scipy(so.state_to_matrix(
+        so.fold_events(ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 2], ev[:, 3]), fmt="csr"))
+    t = D.torch()
+    users = D.to_dev(z["rec_users"].astype(np.int32))
+    Q, k, I = users.numel(), 10, W.n_items
+    for mode in (RT_TOPK_DENSE, RT_TOPK_SPARSE):
+        full_ids, full_sc, full_cnt = D.recommend(X, users, W, k, True, mode)
+        cuts = [0, 37, 90, I]
+        parts = [D.recommend(X, users, W, k, True, mode, cuts[s], cuts[s + 1]) for s in range(3)]
+        ids = t.stack([p[0] for p in parts]).contiguous()
+        sc = t.stack([p[1] for p in parts]).contiguous()
+        m_ids, m_sc, m_cnt = D.topk_merge(ids, sc, 3, Q, k)
+        assert t.equal(m_cnt, full_cnt)
+        assert t.equal(m_ids, full_ids)
+        assert t.equal(m_sc, full_sc)
