@@ -164,6 +164,8 @@ class BaseModel(ABC):
         if not cold_slots:
             batch = self._recommend_hot_batch(hot_ids, candidate_item_ids=candidate_item_ids, users_tags=users_tags,
                                               top_k=top_k, filter_interacted=filter_interacted)
+            if self.item_ids.pass_through:
+                return batch  # integer ids map to themselves (identifiers.py:69-72)
             return [[to_items(i) for i in row] for row in batch]
         results: List[List[Any]] = [[] for _ in users]
         cold_tags = [users_tags[s] for s in cold_slots] if users_tags else None

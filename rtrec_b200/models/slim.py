@@ -77,7 +77,8 @@ class SLIM(BaseModel):
         dense_output = not self.item_ids.pass_through
         ids, _, cnt = self.model.recommend_batch_device(np.asarray(user_ids, dtype=np.int64), X, candidate_item_ids,
                                                         top_k, filter_interacted, dense_output)
-        return [ids[r, :int(cnt[r])].tolist() for r in range(len(user_ids))]
+        rows = ids.tolist()
+        return [row[:c] for row, c in zip(rows, cnt.tolist())]
 
     def _similar_items(self, query_item_id: int, query_item_tags: Optional[List[str]] = None, top_k: int = 10) -> List[Tuple[int, float]]:
         """slim.py:106-115."""

@@ -128,11 +128,15 @@ class UserItemInteractions:
         self._seal_scalars()
         self._pend.append((u.astype(np.int32), i.astype(np.int32), ts, d))
         self._pend_n += n
-        self.all_item_ids.update(np.unique(i).tolist())
+        imax = int(i.max())
+        if imax < 8 * n + (1 << 20):
+            self.all_item_ids.update(np.flatnonzero(np.bincount(i)).tolist())
+        else:
+            self.all_item_ids.update(np.unique(i).tolist())
         pos = d > 0
         self.hot_items.add_batch(i[pos] if not pos.all() else i)
         self.max_user_id = max(self.max_user_id, int(u.max()))
-        self.max_item_id = max(self.max_item_id, int(i.max()))
+        self.max_item_id = max(self.max_item_id, imax)
         self._touch()
         if self._pend_n >= _FLUSH_AT:
             self._flush()

@@ -56,7 +56,18 @@ class LRUFreqSet(MutableSet):
         if n == 0:
             return
         values = np.asarray(values)
-        uniq, inv, counts = np.unique(values, return_inverse=True, return_counts=True)
+        if values.dtype.kind in "iu" and values.min() >= 0 and int(values.max()) < 8 * n + (1 << 20):
+            # small non-negative ints: O(n) counting instead of a sort
+            dense_counts = np.bincount(values)
+            uniq = np.flatnonzero(dense_counts)
+            counts = dense_counts[uniq]
+            dense_last = np.zeros(len(dense_counts), dtype=np.int64)
+            dense_last[values] = np.arange(n)  # repeated index: the last assignment wins
+            last = dense_last[uniq]
+        else:
+            uniq, inv, counts = np.unique(values, return_inverse=True, return_counts=True)
+            last = np.full(len(uniq), -1, dtype=np.int64)
+            last[inv] = np.arange(n)  # later occurrences overwrite earlier ones
         n_fresh = sum(1 for k in uniq.tolist() if k not in self.data)
         if len(self.data) + n_fresh > self.capacity:
             # an eviction can happen somewhere inside the batch: replay it event by event
@@ -64,8 +75,6 @@ class LRUFreqSet(MutableSet):
                 self.add(v)
             return
         # no eviction: counters add up, touched keys move to the MRU end ordered by last touch
-        last = np.full(len(uniq), -1, dtype=np.int64)
-        last[inv] = np.arange(n)  # later occurrences overwrite earlier ones
         for j in np.argsort(last, kind="stable").tolist():
             key = uniq[j].item()
             self.data[key] = self.data.pop(key, 0) + int(counts[j])
