@@ -1,0 +1,57 @@
+"""Summarise an .ncu-rep (captured with `ncu --set full`) into a small markdown table for profiles/.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_xxx.md "title"
+"""
+import csv, subprocess, sys, io
+
+METRICS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("launch__registers_per_thread", "registers/thread"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+]
+
+
+def main():
+    rep, out, title = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "")
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(out, "w") as f:
+        f.write(f"# {title}\n\nSource: `{rep}` (ncu --set full --clock-control none), one column per captured launch.\n\n")
+        names = [r[idx["Kernel Name"]].split("(")[0] for r in data]
+        f.write("| metric | " + " | ".join(names) + " |\n|---|" + "---|" * len(names) + "\n")
+        for key, label in METRICS:
+            if key not in idx:
+                continue
+            vals = []
+            for r in data:
+                v = r[idx[key]]
+                try:
+                    v = f"{float(v):,.3f}".rstrip("0").rstrip(".")
+                except ValueError:
+                    pass
+                vals.append(f"{v} {units[idx[key]]}".strip())
+            f.write(f"| {label} (`{key}`) | " + " | ".join(vals) + " |\n")
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()
