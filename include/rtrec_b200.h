@@ -111,6 +111,24 @@ int rt_gram_rows(const int32_t *d_ccol, const int32_t *d_cidx, const float *d_cv
                  int64_t e_end, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
                  float *d_G, int64_t ldg, void *stream);
 
+/*
+ * Same result as rt_gram_rows for the target columns [j_begin, j_end) of the CSC matrix, computed
+ * with warp-private shared-memory accumulators instead of global atomics (gram2.cu): per (j, i)
+ * the fp32 sum runs in ascending user order like scipy's csr_matvec (slim_elastic.py:141).
+ * G rows being produced must be zero-filled by the caller.  Synchronises the stream.
+ */
+int rt_gram(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+            const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+            int32_t j_begin, int32_t j_end, float *d_G, int64_t ldg, void *stream);
+
+/*
+ * Range-split row pointers of a CSR/CSC matrix with ascending minor indices:
+ * d_seg[row * (n_ranges + 1) + g] = first position of `row` whose minor index is
+ * >= base + g * range_width.  Helper of rt_gram; exported for tests.
+ */
+int rt_csr_split(int32_t n_rows, const int32_t *d_ptr, const int32_t *d_idx, int32_t base,
+                 int32_t range_width, int32_t n_ranges, int32_t *d_seg, void *stream);
+
 typedef struct {
     double alpha;        /* SLIMElastic.alpha      (slim_elastic.py:184) */
     double l1_ratio;     /* SLIMElastic.l1_ratio   (:185) */
@@ -214,6 +232,10 @@ int rt_topk_merge(const int32_t *d_ids, const float *d_scores, int32_t n_shards,
 int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d_wval, int32_t n_items,
                     const int32_t *d_items, int32_t n_query, int32_t k, int32_t *d_out_ids,
                     float *d_out_scores, int32_t *d_out_cnt, void *stream);
+
+/* Tuning switches: "score_impl" (1 = first-generation scoring kernel, 2 = staged/pipelined kernel,
+ * default 2).  Returns RT_ERR_ARG for an unknown name. */
+int rt_set_option(const char *name, int32_t value);
 
 /* Frees the library-owned device scratch (grow-only arenas reused across calls). */
 void rt_release_scratch(void);

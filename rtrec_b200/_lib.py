@@ -54,6 +54,8 @@ PROTOTYPES = {
                                  C.POINTER(_I64), C.POINTER(C.c_int), _P]),
     "rt_store_lookup": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),
     "rt_gram_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _I64, _P]),
+    "rt_gram": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
+    "rt_csr_split": (C.c_int, [_I32, _P, _P, _I32, _I32, _I32, _P, _P]),
     "rt_rng_table": (C.c_int, [_U32, _I64, _P, _P]),
     "rt_slim_solve": (C.c_int, [_P, _I64, _I32, _P, _I32, C.POINTER(FitConfig), _P, _P, _I64, _P, _P, _P, _P, _P, _I64,
                                 C.POINTER(_I64), _P, _P]),
@@ -63,6 +65,7 @@ PROTOTYPES = {
     "rt_slim_recommend_candidates": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P]),
     "rt_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rt_slim_similar": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P]),
+    "rt_set_option": (C.c_int, [C.c_char_p, _I32]),
     "rt_release_scratch": (None, []),
     "rt_launch_count": (_I64, []),
     "rt_launch_count_reset": (None, []),

@@ -1,5 +1,6 @@
 // api.cu -- library-wide plumbing of librtrec_b200: error string, device info, launch counter.
 #include <stdarg.h>
+#include <string.h>
 #include <atomic>
 
 #include "common.cuh"
@@ -65,6 +66,9 @@ void *scratch(int slot, size_t bytes) {
     return p;
 }
 
+static int g_opts[OPT_COUNT] = {2, 2};
+int option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_opts[key] : 0; }
+
 int sm_count() { return query_device() == RT_OK ? g_sm_count : 148; }
 int smem_optin() { return query_device() == RT_OK ? g_smem_optin : 232448; }
 
@@ -80,6 +84,13 @@ extern "C" int rt_device_info(int *sm_count, int *smem_optin_bytes, int *cc_majo
     if (cc_major) *cc_major = rt::g_cc_major;
     if (cc_minor) *cc_minor = rt::g_cc_minor;
     return RT_OK;
+}
+extern "C" int rt_set_option(const char *name, int32_t value) {
+    if (!name) { rt::set_error("rt_set_option: null name"); return RT_ERR_ARG; }
+    if (!strcmp(name, "score_impl")) { rt::g_opts[rt::OPT_SCORE_IMPL] = value; return RT_OK; }
+    if (!strcmp(name, "gram_impl")) { rt::g_opts[rt::OPT_GRAM_IMPL] = value; return RT_OK; }
+    rt::set_error("rt_set_option: unknown option '%s'", name);
+    return RT_ERR_ARG;
 }
 extern "C" void rt_release_scratch(void) {
     cudaDeviceSynchronize();

@@ -12,6 +12,9 @@ void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
 int smem_optin();
+// tuning switches settable through rt_set_option(): which kernel generation serves an entry point
+enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_COUNT };
+int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).
 void *scratch(int slot, size_t bytes);
@@ -61,6 +64,16 @@ struct Carver {
     bool ok() const { return off <= cap; }
 };
 
+}  // namespace rt
+// v2 scoring kernel launcher (score2.cu), called by rt_slim_recommend
+int rt_launch_recommend2(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval, const int32_t *d_users,
+                         int32_t n_query, const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval,
+                         int32_t n_items, int32_t j_begin, int32_t j_end, int32_t k, int32_t filter_interacted,
+                         int32_t mode, int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt, int *d_next,
+                         cudaStream_t st);
+extern "C" int rt_csr_split(int32_t n_rows, const int32_t *d_ptr, const int32_t *d_idx, int32_t base,
+                            int32_t range_width, int32_t n_ranges, int32_t *d_seg, void *stream);
+namespace rt {
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t float_key(float f) {
     // order-preserving map float -> uint32 (larger float => larger key); -0.0 folded into +0.0

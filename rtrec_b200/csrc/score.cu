@@ -247,6 +247,9 @@ extern "C" int rt_slim_recommend(const int32_t *d_rptr, const int32_t *d_ridx, c
         RT_CUDA(cudaMemsetAsync(d_out_scores, 0, sizeof(float) * (size_t)n_query * k, st));
         return RT_OK;
     }
+    if (rt::option(rt::OPT_SCORE_IMPL) != 1)  // 1 = first-generation kernel below (kept for A/B timing)
+        return rt_launch_recommend2(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, n_items, j_begin,
+                                    j_end, k, filter_interacted, mode, d_out_ids, d_out_scores, d_out_cnt, d_next, st);
     // tile: as much of the item range as fits next to the static shared memory; prefer two CTAs/SM
     const int optin = rt::smem_optin();
     const int static_bytes = (int)sizeof(ScoreShared) + 1024;

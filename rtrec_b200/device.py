@@ -183,6 +183,22 @@ def gram(X: DeviceMatrix, e_begin: int = 0, e_end: Optional[int] = None, out=Non
     return out
 
 
+def gram_cols(X: DeviceMatrix, j_begin: int = 0, j_end: Optional[int] = None, out=None):
+    """Gram rows of the target columns [j_begin, j_end) with shared-memory accumulators (rt_gram)."""
+    t = require_cuda()
+    I = X.n_items
+    if out is None:
+        out = t.zeros((I, I), dtype=t.float32, device=dev())
+    j_end = I if j_end is None else j_end
+    check(_lib.load().rt_gram(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx), ptr(X.rval),
+                              int(j_begin), int(j_end), ptr(out), I, stream_ptr()), "rt_gram")
+    return out
+
+
+def set_option(name: str, value: int) -> None:
+    check(_lib.load().rt_set_option(name.encode(), int(value)), "rt_set_option")
+
+
 @dataclass
 class SolveResult:
     targets: object   # int32 device [T]
