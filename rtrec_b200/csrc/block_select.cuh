@@ -167,4 +167,156 @@ __device__ int block_top_n(int N, int n, KeyFn key_of, EligFn eligible, SelectSc
     return cnt;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: threshold from bucket maxima.
+//
+// key_of(idx) returns an order-preserving key, 0 meaning "not eligible".  128 strided buckets
+// (bucket = idx mod 128) each remember their largest key; the n-th largest bucket maximum T is a
+// lower bound of the n-th largest key (n distinct elements are >= T).  Everything > T is
+// collected (normally little more than n elements); if fewer than n are strictly greater, the
+// remaining picks are the elements == T with the largest indices, found by scanning from the top
+// index down and stopping early.  The list is rank-sorted by (key desc, idx desc), so the result is
+// exactly what block_top_n returns; block_top_n itself is the fallback when the list overflows,
+// n > 128 or the block is not a multiple of 128 threads.  Two light passes over the data.
+constexpr int FS_BUCKETS = 128;
+constexpr int FS_LIST = 512;
+
+struct FastSelScratch {
+    union {
+        struct {
+            uint32_t bmax[FS_BUCKETS];
+            uint32_t lkey[FS_LIST];
+            int lidx[FS_LIST];
+        } f;
+        struct {
+            SelectScratch sel;
+            uint32_t cand_key[FS_BUCKETS];
+            int cand_idx[FS_BUCKETS];
+        } x;  // exact fallback (n <= 128); larger n uses caller-provided global temporaries
+    } u;
+    int wtot[2][32];
+    int cnt_gt, cnt_ge;
+    uint32_t T;
+};
+
+// out_idx/out_key: capacity >= n, CTA-visible.  big_key/big_idx: temporaries of capacity >= n for the
+// exact path when n > 128 (may be null if n <= 128).  Returns min(n, #eligible).
+template <typename KeyFn>
+__device__ int block_top_n_fast(int N, int n, KeyFn key_of, FastSelScratch *fs, int *out_idx, uint32_t *out_key,
+                                uint32_t *big_key = nullptr, int *big_idx = nullptr) {
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = (NT + 31) >> 5;
+    if (n <= 0 || N <= 0) return 0;
+    auto exact = [&]() -> int {
+        auto elig = [&](int, uint32_t key) -> bool { return key != 0u; };
+        __syncthreads();
+        const int c = block_top_n(N, n, key_of, elig, &fs->u.x.sel, n <= FS_BUCKETS ? fs->u.x.cand_key : big_key,
+                                  n <= FS_BUCKETS ? fs->u.x.cand_idx : big_idx, out_idx, out_key);
+        __syncthreads();
+        return c;
+    };
+    if (n > FS_BUCKETS || (NT % FS_BUCKETS) != 0 || N < 4 * FS_BUCKETS) return exact();
+    // ---- pass 1: bucket maxima and eligible count -------------------------------------------------
+    __syncthreads();
+    if (tid < FS_BUCKETS) fs->u.f.bmax[tid] = 0u;
+    if (tid == 0) { fs->cnt_gt = 0; fs->cnt_ge = 0; }
+    __syncthreads();
+    uint32_t m = 0u;
+    int ne = 0;
+    for (int x = tid; x < N; x += NT) {
+        const uint32_t key = key_of(x);
+        m = max(m, key);
+        ne += key != 0u;
+    }
+    if (m) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], m);
+    ne = warp_sum_i(ne);
+    if (lane == 0) fs->wtot[0][warp] = ne;
+    __syncthreads();
+    int n_elig = 0;
+    for (int w = 0; w < nwarps; ++w) n_elig += fs->wtot[0][w];
+    const int kk = min(n, n_elig);
+    if (kk == 0) return 0;
+    if (tid < FS_BUCKETS) {
+        const uint32_t bm = fs->u.f.bmax[tid];
+        int rank = 0;
+        for (int f = 0; f < FS_BUCKETS; ++f) {
+            const uint32_t kf = fs->u.f.bmax[f];
+            rank += (kf > bm) || (kf == bm && f < tid);
+        }
+        if (rank == kk - 1) fs->T = bm == 0u ? 1u : bm;
+    }
+    __syncthreads();
+    const uint32_t T = fs->T;
+    // ---- pass 2: collect everything >= T (also count how many are strictly above) ------------------
+    auto collect = [&](bool strict) {
+        for (int base = 0; base < N; base += NT) {
+            const int x = base + tid;
+            uint32_t key = 0u;
+            if (x < N) key = key_of(x);
+            const bool gt = key > T;
+            const bool take = strict ? gt : key >= T;
+            const unsigned bal = __ballot_sync(0xffffffffu, take);
+            if (bal) {
+                const unsigned bgt = __ballot_sync(0xffffffffu, gt);
+                int basepos = 0;
+                if (lane == 0) {
+                    basepos = atomicAdd(&fs->cnt_ge, __popc(bal));
+                    if (bgt) atomicAdd(&fs->cnt_gt, __popc(bgt));
+                }
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                const int pos = take ? basepos + __popc(bal & ((1u << lane) - 1u)) : FS_LIST;
+                if (pos < FS_LIST) { fs->u.f.lkey[pos] = key; fs->u.f.lidx[pos] = x; }
+            }
+        }
+        __syncthreads();
+    };
+    collect(false);
+    int total = fs->cnt_ge;
+    if (total > FS_LIST) {
+        // too many ties at T (or T far below the n-th key): keep only the strictly larger ones ...
+        const int c_gt = fs->cnt_gt;
+        if (c_gt > FS_LIST) return exact();
+        __syncthreads();
+        if (tid == 0) { fs->cnt_ge = 0; fs->cnt_gt = 0; }
+        __syncthreads();
+        collect(true);
+        total = c_gt;
+        if (c_gt < kk) {
+            // ... and take the (kk - c_gt) largest indices among the ties, scanning downwards
+            const int need = kk - c_gt;
+            int taken = 0, buf = 0;
+            for (int top = ((N + NT - 1) / NT) * NT; top > 0 && taken < need; top -= NT, buf ^= 1) {
+                const int x = top - 1 - tid;  // thread order = descending index
+                const bool eq = x < N && key_of(x) == T;
+                const unsigned bal = __ballot_sync(0xffffffffu, eq);
+                if (lane == 0) fs->wtot[buf][warp] = __popc(bal);
+                __syncthreads();
+                int off = taken, tot = 0;
+                for (int w = 0; w < nwarps; ++w) { const int c = fs->wtot[buf][w]; if (w < warp) off += c; tot += c; }
+                if (eq) {
+                    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < need) { fs->u.f.lkey[c_gt + pos] = T; fs->u.f.lidx[c_gt + pos] = x; }
+                }
+                taken += tot;
+            }
+            total = kk;
+            __syncthreads();
+        }
+    }
+    // ---- rank sort ------------------------------------------------------------------------------
+    for (int e = tid; e < total; e += NT) {
+        const uint32_t ke = fs->u.f.lkey[e];
+        const int ie = fs->u.f.lidx[e];
+        int rank = 0;
+        for (int f = 0; f < total; ++f) {
+            const uint32_t kf = fs->u.f.lkey[f];
+            const int jf = fs->u.f.lidx[f];
+            rank += (kf > ke) || (kf == ke && jf > ie);
+        }
+        if (rank < kk) { out_idx[rank] = ie; if (out_key) out_key[rank] = ke; }
+    }
+    __syncthreads();
+    return kk;
+}
+
 }  // namespace rt

@@ -26,24 +26,19 @@ namespace rt {
 
 constexpr int S2_NT = 512;      // threads per CTA (2 CTAs/SM at the ML-20M tile size)
 constexpr int S2_CH = 512;      // interacted items staged per chunk
-constexpr int S2_LIST = 512;    // candidate list capacity of the fast top-k
-constexpr int S2_NB = 128;      // bucket maxima used for the threshold (>= KMAX2)
 constexpr int S2_GROUP = 8;     // rows whose head entries are fetched together
 constexpr int KMAX2 = 128;
 
 struct Score2Shared {
     union {
-        struct { int a[S2_CH]; int b[S2_CH]; float x[S2_CH]; } st;                       // staging
-        struct { uint32_t tmax[S2_NT]; uint32_t lkey[S2_LIST]; int lidx[S2_LIST]; } tk;   // fast top-k
-        struct { SelectScratch sel; uint32_t cand_key[KMAX2]; int cand_idx[KMAX2];
-                 uint32_t out_key[KMAX2]; int out_idx[KMAX2]; } fb;                       // exact fallback
-        struct { uint32_t key[2 * KMAX2]; int idx[2 * KMAX2]; } tmp;                      // tile merge
+        struct { int a[S2_CH]; int b[S2_CH]; float x[S2_CH]; } st;    // staging
+        FastSelScratch fs;                                             // top-k
+        struct { uint32_t key[2 * KMAX2]; int idx[2 * KMAX2]; } tmp;   // tile merge
     } u;
     uint32_t best_key[2 * KMAX2];
     int best_idx[2 * KMAX2];
-    int wsum[2][32];
-    int n_rows, q, cnt, n_elig;
-    uint32_t T;
+    int wsum[32];
+    int n_rows, q;
 };
 
 __device__ __forceinline__ float key_to_float2(uint32_t k) {
@@ -106,11 +101,11 @@ recommend2_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                     }
                     const bool ne = b > a;
                     const unsigned bal = __ballot_sync(0xffffffffu, ne);
-                    if (lane == 0) sh.wsum[0][warp] = __popc(bal);
+                    if (lane == 0) sh.wsum[warp] = __popc(bal);
                     __syncthreads();
                     int off = 0, tot = 0;
 #pragma unroll
-                    for (int w = 0; w < NW; ++w) { const int c = sh.wsum[0][w]; if (w < warp) off += c; tot += c; }
+                    for (int w = 0; w < NW; ++w) { const int c = sh.wsum[w]; if (w < warp) off += c; tot += c; }
                     if (ne) {
                         const int s = off + __popc(bal & ((1u << lane) - 1u));
                         sh.u.st.a[s] = a; sh.u.st.b[s] = b; sh.u.st.x[s] = x;
@@ -153,91 +148,12 @@ recommend2_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                 __syncthreads();
             }
             // ---------------- top-k of the tile ----------------
-            // pass 1: strided maxima + eligible count
-            uint32_t m = 0u;
-            int ne = 0;
-            for (int x = tid; x < width; x += S2_NT) {
-                const uint32_t key = elig_key(acc[x], mode);
-                m = max(m, key);
-                ne += key != 0u;
-            }
-            sh.u.tk.tmax[tid] = m;
-            ne = warp_sum_i(ne);
-            if (lane == 0) sh.wsum[1][warp] = ne;
-            if (tid == 0) sh.cnt = 0;
-            __syncthreads();
-            int n_elig = 0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) n_elig += sh.wsum[1][w];
-            const int kk = min(k, n_elig);
-            int c = 0;  // entries appended to best[] by this tile
-            if (kk > 0) {
-                // bucket maxima: bucket = tid mod 128; T = kk-th largest bucket maximum (or 1 = "everything")
-                // (writes go to [0,128), cross-thread reads to [128,512): no hazard inside this step)
-                if (tid < S2_NB) {
-                    uint32_t bm = m;
-#pragma unroll
-                    for (int o = S2_NB; o < S2_NT; o += S2_NB) bm = max(bm, sh.u.tk.tmax[tid + o]);
-                    m = bm;
-                    sh.u.tk.tmax[tid] = bm;
-                }
+            auto key_of = [&](int idx) -> uint32_t { return elig_key(acc[idx], mode); };
+            // the tile's list is appended to best[] (capacity 2k); indices become global item ids
+            const int c = block_top_n_fast(width, k, key_of, &sh.u.fs, sh.best_idx + nbest, sh.best_key + nbest);
+            if (t0 != 0) {
+                for (int e = tid; e < c; e += S2_NT) sh.best_idx[nbest + e] += t0;
                 __syncthreads();
-                if (tid < S2_NB) {
-                    int rank = 0;
-                    for (int f = 0; f < S2_NB; ++f) {
-                        const uint32_t kf = sh.u.tk.tmax[f];
-                        rank += (kf > m) || (kf == m && f < tid);
-                    }
-                    if (rank == kk - 1) sh.T = m == 0u ? 1u : m;
-                }
-                __syncthreads();
-                const uint32_t T = sh.T;
-                // pass 2: collect everything >= T
-                for (int base = 0; base < width; base += S2_NT) {
-                    const int x = base + tid;
-                    uint32_t key = 0u;
-                    if (x < width) key = elig_key(acc[x], mode);
-                    const bool take = key >= T;  // T >= 1, so ineligible scores never pass
-                    const unsigned bal = __ballot_sync(0xffffffffu, take);
-                    if (bal) {
-                        int basepos = 0;
-                        if (lane == 0) basepos = atomicAdd(&sh.cnt, __popc(bal));
-                        basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                        if (take) {
-                            const int pos = basepos + __popc(bal & ((1u << lane) - 1u));
-                            if (pos < S2_LIST) { sh.u.tk.lkey[pos] = key; sh.u.tk.lidx[pos] = x; }
-                        }
-                    }
-                }
-                __syncthreads();
-                const int cnt = sh.cnt;
-                if (cnt <= S2_LIST) {
-                    // rank sort of the list by (key desc, idx desc); the first kk go to best[]
-                    for (int e = tid; e < cnt; e += S2_NT) {
-                        const uint32_t ke = sh.u.tk.lkey[e];
-                        const int ie = sh.u.tk.lidx[e];
-                        int rank = 0;
-                        for (int f = 0; f < cnt; ++f) {
-                            const uint32_t kf = sh.u.tk.lkey[f];
-                            const int jf = sh.u.tk.lidx[f];
-                            rank += (kf > ke) || (kf == ke && jf > ie);
-                        }
-                        if (rank < kk) { sh.best_key[nbest + rank] = ke; sh.best_idx[nbest + rank] = ie + t0; }
-                    }
-                    c = kk;
-                    __syncthreads();
-                } else {
-                    // massive ties: exact radix select (slow path, same order)
-                    __syncthreads();
-                    auto key_of = [&](int idx) -> uint32_t { return elig_key(acc[idx], mode); };
-                    auto elig = [&](int, uint32_t key) -> bool { return key != 0u; };
-                    c = block_top_n(width, k, key_of, elig, &sh.u.fb.sel, sh.u.fb.cand_key, sh.u.fb.cand_idx,
-                                    sh.u.fb.out_idx, sh.u.fb.out_key);
-                    for (int e = tid; e < c; e += S2_NT) {
-                        sh.best_key[nbest + e] = sh.u.fb.out_key[e]; sh.best_idx[nbest + e] = sh.u.fb.out_idx[e] + t0;
-                    }
-                    __syncthreads();
-                }
             }
             // merge with the running best of earlier tiles
             const int tot = nbest + c;

@@ -48,7 +48,7 @@ struct SolveArgs {
 };
 
 struct Misc {
-    SelectScratch sel;
+    FastSelScratch fsel;
     double red[4][32];
     int wtot[2][2][32];
     int t;
@@ -81,7 +81,7 @@ __device__ __forceinline__ void block_sum4(double &v0, double &v1, double &v2, d
     for (int w = 1; w < nw; ++w) { v0 += ms->red[0][w]; v1 += ms->red[1][w]; v2 += ms->red[2][w]; v3 += ms->red[3][w]; }
 }
 
-__global__ void __launch_bounds__(256) slim_solve_kernel(SolveArgs A) {
+__global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
     extern __shared__ __align__(16) char dyn_smem[];
     __shared__ Misc ms;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(256) slim_solve_kernel(SolveArgs A) {
                 for (int k = tid; k < NU; k += NT) feat[k] = A.sel_in[(size_t)t * A.nn + k];
                 __syncthreads();
             } else {
+                // every item is eligible (float_key is never 0); the target itself scores 0 (its column is zeroed)
                 auto key_of = [&](int i) -> uint32_t { return float_key(i == j ? 0.0f : gj[i]); };
-                auto elig = [&](int, uint32_t) -> bool { return true; };
-                block_top_n(A.n_items, NU, key_of, elig, &ms.sel, ckey, cidx, feat, (uint32_t *)nullptr);
+                block_top_n_fast(A.n_items, NU, key_of, &ms.fsel, feat, (uint32_t *)nullptr, ckey, cidx);
             }
             if (A.sel_out) {
                 for (int k = tid; k < A.nn; k += NT) A.sel_out[(size_t)t * A.nn + k] = k < NU ? feat[k] : -1;
@@ -508,9 +508,9 @@ SolvePlan make_plan(int n_items, int nn, int n_targets) {
     p.cold_bytes = cold;
     p.smem_bytes = p.hot_in_smem ? hot : 0;
     p.scratch_per_cta = rt::align_up(cold + (p.hot_in_smem ? 0 : hot) + 256, 256);
-    p.NT = nn > 0 ? 64 : 128;
+    p.NT = 128;  // multiple of 128: the fast candidate selection uses 128 strided buckets
     // resident CTAs per SM, bounded by shared memory
-    int per_sm = nn > 0 ? 16 : 4;
+    int per_sm = nn > 0 ? 8 : 4;
     if (p.hot_in_smem) {
         int fit = (int)(((size_t)optin) / (hot + static_smem + 1024));
         if (fit < 1) fit = 1;
