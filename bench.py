@@ -194,24 +194,16 @@ def run_ours(args):
         mark("store_build")
         cfg = op._config(X)
         t = torch
-        G = t.zeros((X.n_items, X.n_items), dtype=t.float32, device="cuda")
-        mark("gram_zero")
         cptr_host = X.cptr.cpu().numpy() if world > 1 else None
         j0, j1 = P.item_shard(X.n_items, rank, world, cptr_host)
-        if world == 1:
-            D.gram(X, out=G)
-            mark("gram_rows")
-        else:
-            D.gram(X, int(cptr_host[j0]), int(cptr_host[j1]), out=G)
-            mark("gram_rows")
-            works = []
-            for rr in range(world):
-                a, b = P.item_shard(X.n_items, rr, world, cptr_host)
-                if b > a:
-                    works.append(dist.broadcast(G[a:b], src=rr, async_op=True))
-            for w in works:
-                w.wait()
+        L = D.gram_lower(X, part=rank, n_parts=world)
+        mark("gram_lower")
+        if world > 1:
+            P.exchange_slabs(L.Gp, L.cuts)
             mark("gram_exchange")
+        G = D.gram_finish(L)
+        del L
+        mark("gram_finish")
         tg = t.arange(j0, j1, dtype=t.int32, device="cuda")
         res = D.solve(G, X.n_items, tg, cfg)
         mark("solve")
@@ -279,18 +271,18 @@ def run_ours(args):
     wr = np.diff(W.wrptr.cpu().numpy()).astype(np.float64)
     ridx = X.ridx[:X.nnz].cpu().numpy()
     rec_bytes = e_bytes * X.nnz + e_bytes * float(wr[ridx].sum()) + 8.0 * TOP_K * U
-    kern = {"gram_rows": (phase_ms.get("gram_rows", 0.0), gram_bytes), "recommend": (rec_ms, rec_bytes)}
-    dom = max(phase_ms, key=lambda k: phase_ms[k])
-    roofline = None
-    if dom in kern and kern[dom][0] > 0:
-        ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": kern[dom][1], "ms_per_launch": round(kern[dom][0], 3)}
-    else:
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                    "traffic": None, "peak_source": peak_src,
-                    "note": "dominant phase is latency/occupancy bound (sequential coordinate descent); see DESIGN.md"}
+    # K4 (Gram form): one G row scanned for the candidate selection + the live x live block gathered + output pairs
+    nn = kwargs.get("nn_feature_selection") or X.n_items
+    m_live = stats[:, 3]
+    solve_bytes = float((4.0 * X.n_items + 4.0 * (m_live * m_live + m_live) + e_bytes * nn).sum())
+    gram_ms = phase_ms.get("gram_lower", 0.0) + phase_ms.get("gram_finish", 0.0)
+    kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0), solve_bytes), "recommend": (rec_ms, rec_bytes)}
+    dom = max(kern, key=lambda k: kern[k][0])
+    ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kern[dom][1], "ms_per_launch": round(kern[dom][0], 3),
+                "note": "gram = rt_gram_lower + rt_gram_finish (rank/sort/prefix kernels included); bytes per SURVEY.md 8(d)"}
     other = {k: {"ms": round(v[0], 3), "GBps": round(v[1] / (v[0] / 1e3) / 1e9, 1) if v[0] > 0 else None} for k, v in kern.items()}
 
     # ---- e2e through the public API with host buffers (rank 0 only at N=1; all ranks otherwise skip)

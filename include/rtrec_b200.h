@@ -122,6 +122,23 @@ int rt_gram(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32
             int32_t j_begin, int32_t j_end, float *d_G, int64_t ldg, void *stream);
 
 /*
+ * Third-generation Gram (gram3.cu), the default fit path.  Items are relabelled by popularity rank
+ * (count desc, id asc); rt_gram_lower computes the rows [h_cuts[part], h_cuts[part+1]) of the
+ * LOWER triangle of G' = X'^T X' in rank space into d_Gp (zero-filled by the caller, ld = ldgp),
+ * where the n_parts row ranges are balanced by exact multiply-add count; d_rank_of / d_orig_of
+ * (int32[n_items]) receive the permutation.  With n_parts > 1 the caller exchanges the row slabs
+ * (all-gather) before rt_gram_finish, which mirrors the triangle in place and writes the full
+ * symmetric G in the caller's item ids to d_G (every entry is written; d_G != d_Gp).
+ * rt_gram_lower synchronises only when n_parts > 1 (to return h_cuts[n_parts + 1]).
+ */
+int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                  const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                  int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
+                  int32_t *d_orig_of, int32_t *h_cuts, void *stream);
+int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                   const int32_t *d_orig_of, float *d_G, int64_t ldg, void *stream);
+
+/*
  * Range-split row pointers of a CSR/CSC matrix with ascending minor indices:
  * d_seg[row * (n_ranges + 1) + g] = first position of `row` whose minor index is
  * >= base + g * range_width.  Helper of rt_gram; exported for tests.

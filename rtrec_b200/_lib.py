@@ -55,6 +55,8 @@ PROTOTYPES = {
     "rt_store_lookup": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),
     "rt_gram_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, _P, _I64, _P]),
     "rt_gram": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
+    "rt_gram_lower": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, C.POINTER(_I32), _P]),
+    "rt_gram_finish": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P]),
     "rt_csr_split": (C.c_int, [_I32, _P, _P, _I32, _I32, _I32, _P, _P]),
     "rt_rng_table": (C.c_int, [_U32, _I64, _P, _P]),
     "rt_slim_solve": (C.c_int, [_P, _I64, _I32, _P, _I32, C.POINTER(FitConfig), _P, _P, _I64, _P, _P, _P, _P, _P, _I64,

@@ -1,0 +1,406 @@
+// gram3.cu -- K3 (v3): item-item Gram matrix G = X^T X by popularity-ranked lower triangle.
+//
+// Replaces the per-column `X.T.dot(y)` of FeatureSelectionWrapper.fit
+// (/root/reference/rtrec/models/internal/slim_elastic.py:141) for ALL target columns at once and
+// produces the Gram matrix the solver replays on (solve.cu).  Same values as gram.cu / gram2.cu.
+//
+// Why a third generation (profiles/r1a_*, r1c_*): v1 issues one global fp32 RED per multiply-add
+// (RED-issue bound, 28 GB of DRAM writes for a 2.9 GB matrix); v2 keeps warp-private accumulators
+// in shared memory but, with item ids in arbitrary order, most (rater, item-range) segments hold a
+// handful of entries, so 3 of 4 lanes idle.  v3 fixes the layout first:
+//
+//   1. items are relabelled by popularity rank (most rated first).  In rank space the matrix is
+//      dense in the top-left corner and sparse elsewhere, whatever the id order of the caller;
+//   2. G is symmetric, so only the lower triangle G'[j', i' <= j'] is computed: a rater u of item
+//      j' contributes x_uj * (the prefix of its rank-sorted row up to j').  Half the work, and the
+//      prefix of a row is one contiguous, coalesced stream;
+//   3. the head of every row (ranks < R*RW) is accumulated in warp-private shared-memory slices
+//      (no atomics, ascending-user summation order = scipy's csr_matvec order); the sparse tail
+//      (ranks >= R*RW, short segments) goes to global memory with fp32 RED;
+//   4. a tiled transpose mirrors the triangle, and a row-staged gather writes G back in the
+//      caller's item ids, so nothing downstream knows about ranks.
+//
+// Multi-GPU: rows of G' are split between ranks by exact multiply-add count; each rank computes
+// its slab (rt_gram_lower), slabs are all-gathered by the caller, every rank finishes locally
+// (rt_gram_finish).
+//
+// Algorithmic bytes per target column (SURVEY.md 8d, K3 term): e*(S_j + nnz_j) + 4*n_items written;
+// the symmetric formulation reads half of S_j.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace rt {
+
+constexpr int G3_WARPS = 8;       // warps per CTA
+constexpr int G3_SLICE = 1728;    // floats per warp slice (8 * 1728 * 4 B = 54 KB per CTA, 4 CTAs/SM)
+constexpr int G3_CHUNK = 2048;    // raters per task
+constexpr int G3_MAX_R = 4;       // at most 4 shared-memory ranges (head = R * G3_SLICE ranks)
+
+__global__ void rank_keys_kernel(const int *__restrict__ cptr, int n_items, unsigned long long *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const unsigned cnt = (unsigned)(cptr[i + 1] - cptr[i]);
+    keys[i] = (((unsigned long long)(0xffffffffu - cnt)) << 32) | (unsigned)i;  // count desc, id asc
+}
+
+__global__ void rank_scatter_kernel(const unsigned long long *__restrict__ sorted, int n_items, int *__restrict__ orig_of,
+                                    int *__restrict__ rank_of) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_items) return;
+    const int id = (int)(sorted[r] & 0xffffffffull);
+    orig_of[r] = id;
+    rank_of[id] = r;
+}
+
+// one warp per user row: key = (user << 32 | rank of item)
+__global__ void relabel_keys_kernel(int n_users, const int *__restrict__ rptr, const int *__restrict__ ridx,
+                                    const int *__restrict__ rank_of, unsigned long long *__restrict__ keys) {
+    const int lane = threadIdx.x & 31;
+    const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (u >= n_users) return;
+    const unsigned long long hi = ((unsigned long long)(unsigned)u) << 32;
+    for (int p = rptr[u] + lane; p < rptr[u + 1]; p += 32) keys[p] = hi | (unsigned)rank_of[ridx[p]];
+}
+
+__global__ void low32_kernel(const unsigned long long *__restrict__ keys, int64_t n, int *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)(keys[i] & 0xffffffffull);
+}
+
+// one thread per stored entry e = (u, j): position of rank(j) inside the rank-sorted row of u; optionally
+// the exact multiply-add count of every rank-column (sum of prefix lengths) for the multi-GPU partition
+__global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict__ rank_of, const int *__restrict__ cptr,
+                                 const int *__restrict__ cidx, const int *__restrict__ rptr, const int *__restrict__ pidx,
+                                 int *__restrict__ cpos, unsigned long long *__restrict__ cost) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < nnz;
+    int jp = -1;
+    unsigned long long work = 0;
+    if (valid) {
+        // column of entry e: last j with cptr[j] <= e
+        int lo = 0, hi = n_items;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cptr[mid] <= (int)e) lo = mid; else hi = mid; }
+        jp = rank_of[lo];
+        const int u = cidx[e];
+        const int a = rptr[u];
+        int l2 = a, h2 = rptr[u + 1];
+        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (pidx[mid] < jp) l2 = mid + 1; else h2 = mid; }
+        cpos[e] = l2;
+        work = (unsigned long long)(l2 - a + 1);
+    }
+    if (cost) {
+        const int j0 = __shfl_sync(0xffffffffu, jp, 0);
+        if (__all_sync(0xffffffffu, jp == j0)) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
+            if ((threadIdx.x & 31) == 0 && j0 >= 0) atomicAdd(&cost[j0], work);
+        } else if (valid) atomicAdd(&cost[jp], work);
+    }
+}
+
+__global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of, const int *__restrict__ cptr,
+                                   int *__restrict__ n_chunks) {
+    const int jp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jp >= n_items) return;
+    const int j = orig_of[jp];
+    n_chunks[jp] = (cptr[j + 1] - cptr[j] + G3_CHUNK - 1) / G3_CHUNK;
+}
+
+__global__ void __launch_bounds__(G3_WARPS * 32)
+gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_start, int R, int RW,
+                  const int *__restrict__ orig_of, const int *__restrict__ cptr, const int *__restrict__ cidx,
+                  const float *__restrict__ cval, const int *__restrict__ cpos, const int *__restrict__ hseg,
+                  const int *__restrict__ pidx, const float *__restrict__ pval, float *__restrict__ Gp, int64_t ld,
+                  unsigned long long *__restrict__ counter) {
+    extern __shared__ __align__(16) float g3_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *slice = g3_smem + (size_t)warp * G3_SLICE;
+    const int n_rows = row_end - row_begin;
+    const int R1 = R + 1;
+    const unsigned long long n_tasks = (unsigned long long)(chunk_start[n_rows] - chunk_start[0]) * (unsigned)R1;
+    const int cs0 = chunk_start[0];
+    for (;;) {
+        unsigned long long task = 0;
+        if (lane == 0) task = atomicAdd(counter, 1ull);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        const int cc = (int)(task / (unsigned)R1) + cs0, g = (int)(task % (unsigned)R1);
+        // row of this chunk: last jr with chunk_start[jr] <= cc
+        int lo_r = 0, hi_r = n_rows;
+        while (hi_r - lo_r > 1) { const int mid = (lo_r + hi_r) >> 1; if (chunk_start[mid] <= cc) lo_r = mid; else hi_r = mid; }
+        const int jp = row_begin + lo_r;
+        const int gj = min(jp / RW, R);  // range that contains jp (R = tail)
+        if (g > gj) continue;
+        const int j = orig_of[jp];
+        const int c0 = cptr[j], c1 = cptr[j + 1];
+        const int e0 = c0 + (cc - chunk_start[lo_r]) * G3_CHUNK;
+        const int e1 = min(e0 + G3_CHUNK, c1);
+        float *g_row = Gp + (size_t)jp * ld;
+        if (g < R) {
+            const int lo = g * RW;
+            const int width = min(RW, jp + 1 - lo);
+            for (int x = lane; x < width; x += 32) slice[x] = 0.0f;
+            __syncwarp();
+            const bool cut = (g == gj);
+            for (int base = e0; base < e1; base += 32) {
+                const int e = base + lane;
+                int a = 0, b = 0;
+                float y = 0.f;
+                if (e < e1) {
+                    const int u = cidx[e];
+                    y = cval[e];
+                    a = hseg[(size_t)u * R1 + g];
+                    b = cut ? cpos[e] + 1 : hseg[(size_t)u * R1 + g + 1];
+                }
+                // Raters are applied one after the other (items of one rater are distinct, so the lanes never
+                // collide in the slice).  Memory latency is hidden by fetching the first 128 entries of the
+                // NEXT rater's segment (4 per lane) before the current one is applied.
+                unsigned mask = __ballot_sync(0xffffffffu, b > a);
+                int nx[4];
+                float nv[4];
+                int n_aa = 0, n_bb = 0;
+                float n_yy = 0.f;
+                auto fetch = [&](int l) {
+                    n_yy = __shfl_sync(0xffffffffu, y, l);
+                    n_aa = __shfl_sync(0xffffffffu, a, l);
+                    n_bb = __shfl_sync(0xffffffffu, b, l);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int p = n_aa + lane + 32 * k;
+                        nx[k] = -1; nv[k] = 0.f;
+                        if (p < n_bb) { nx[k] = pidx[p] - lo; nv[k] = pval[p]; }
+                    }
+                };
+                if (mask) { fetch(__ffs(mask) - 1); mask &= mask - 1; }
+                else continue;
+                for (;;) {
+                    int cx[4];
+                    float cv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { cx[k] = nx[k]; cv[k] = nv[k]; }
+                    const int aa = n_aa, bb = n_bb;
+                    const float yy = n_yy;
+                    const bool more = mask != 0u;
+                    if (more) { fetch(__ffs(mask) - 1); mask &= mask - 1; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (cx[k] >= 0) slice[cx[k]] = __fadd_rn(slice[cx[k]], __fmul_rn(yy, cv[k]));
+                    for (int p = aa + 128 + lane; p < bb; p += 32) {
+                        const int x = pidx[p] - lo;
+                        slice[x] = __fadd_rn(slice[x], __fmul_rn(yy, pval[p]));
+                    }
+                    __syncwarp();
+                    if (!more) break;
+                }
+            }
+            if (c1 - c0 <= G3_CHUNK) {
+                for (int x = lane; x < width; x += 32) g_row[lo + x] = slice[x];
+            } else {
+                for (int x = lane; x < width; x += 32) { const float v = slice[x]; if (v != 0.0f) atomicAdd(g_row + lo + x, v); }
+            }
+            __syncwarp();
+        } else {
+            // tail: ranks in [R*RW, jp], short segments -> global fp32 RED
+            for (int base = e0; base < e1; base += 32) {
+                const int e = base + lane;
+                int a = 0, b = 0;
+                float y = 0.f;
+                if (e < e1) {
+                    const int u = cidx[e];
+                    y = cval[e];
+                    a = hseg[(size_t)u * R1 + R];
+                    b = cpos[e] + 1;
+                }
+                // sub-warp groups of 8 lanes walk 4 entries at a time
+                for (int l0 = 0; l0 < 32; l0 += 4) {
+                    const int src = l0 + (lane >> 3);
+                    const float yy = __shfl_sync(0xffffffffu, y, src);
+                    const int aa = __shfl_sync(0xffffffffu, a, src);
+                    const int bb = __shfl_sync(0xffffffffu, b, src);
+                    for (int p = aa + (lane & 7); p < bb; p += 8) atomicAdd(g_row + pidx[p], __fmul_rn(yy, pval[p]));
+                }
+            }
+        }
+    }
+}
+
+// upper triangle <- transpose of the lower triangle (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) gram_mirror_kernel(float *__restrict__ G, int n, int64_t ld) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int row = by * 32 + r, col = bx * 32 + tx;
+        tile[r][tx] = (row < n && col < n) ? G[(size_t)row * ld + col] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bx * 32 + r, col = by * 32 + tx;  // destination (upper)
+        if (row < n && col < n && col > row) G[(size_t)row * ld + col] = tile[tx][r];
+    }
+}
+
+// G[orig_of[jp]][x] = G'[jp][rank_of[x]]: one CTA per row; the row is staged in shared memory when it fits
+__global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n,
+                                                              const int *__restrict__ rank_of, const int *__restrict__ orig_of,
+                                                              float *__restrict__ G, int64_t ld, int stage) {
+    extern __shared__ __align__(16) float row_s[];
+    const int NT = blockDim.x;
+    for (int jp = blockIdx.x; jp < n; jp += gridDim.x) {
+        const float *src = Gp + (size_t)jp * ldp;
+        float *dst = G + (size_t)orig_of[jp] * ld;
+        if (stage) {
+            __syncthreads();
+#pragma unroll 4
+            for (int x = threadIdx.x; x < n; x += NT) row_s[x] = src[x];
+            __syncthreads();
+#pragma unroll 4
+            for (int x = threadIdx.x; x < n; x += NT) dst[x] = row_s[rank_of[x]];
+        } else {
+#pragma unroll 4
+            for (int x = threadIdx.x; x < n; x += NT) dst[x] = src[rank_of[x]];
+        }
+    }
+}
+
+static int bits_for_n(long long n) { int b = 1; while ((1ll << b) < n && b < 32) ++b; return b; }
+
+}  // namespace rt
+
+using namespace rt;
+
+#define G3_CUB(call_expr)                                                                          \
+    do {                                                                                           \
+        size_t tmp_bytes__ = 0;                                                                    \
+        void *d_tmp__ = nullptr;                                                                   \
+        RT_CUDA(call_expr);                                                                        \
+        d_tmp__ = rt::scratch(SCR_CUB, tmp_bytes__);                                               \
+        if (!d_tmp__) return RT_ERR_CUDA;                                                          \
+        RT_CUDA(call_expr);                                                                        \
+        rt::count_launch(2);                                                                       \
+    } while (0)
+
+extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                             const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                             int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
+                             int32_t *d_orig_of, int32_t *h_cuts, void *stream) {
+    RT_ARG(n_users > 0 && n_items > 0 && nnz >= 0 && nnz < (1ll << 31), "shape");
+    RT_ARG(n_parts >= 1 && part >= 0 && part < n_parts, "part / n_parts");
+    RT_ARG(d_cptr && d_rptr && d_Gp && ldgp >= n_items && d_rank_of && d_orig_of && h_cuts, "null pointer / ldgp");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bs = 256;
+    const int I = n_items;
+    // ---- geometry --------------------------------------------------------------------------------
+    int R = (I + 8 * G3_SLICE - 1) / (8 * G3_SLICE);
+    if (R < 1) R = 1;
+    if (R > G3_MAX_R) R = G3_MAX_R;
+    const int RW = G3_SLICE;
+    // ---- workspace -------------------------------------------------------------------------------
+    Carver sizing(nullptr, (size_t)-1);
+    auto plan = [&](Carver &c) {
+        struct P { unsigned long long *rk, *rks, *keys, *keys2, *cost, *cost_s, *counter; int *pidx, *cpos, *hseg, *n_chunks, *chunk_start; float *pval; } p;
+        p.rk = c.take<unsigned long long>(I); p.rks = c.take<unsigned long long>(I);
+        p.keys = c.take<unsigned long long>(nnz + 1); p.keys2 = c.take<unsigned long long>(nnz + 1);
+        p.cost = c.take<unsigned long long>(I + 1); p.cost_s = c.take<unsigned long long>(I + 1);
+        p.counter = c.take<unsigned long long>(4);
+        p.pidx = c.take<int>(nnz + 1); p.cpos = c.take<int>(nnz + 1); p.hseg = c.take<int>((size_t)n_users * (R + 1));
+        p.n_chunks = c.take<int>(I + 1); p.chunk_start = c.take<int>(I + 2);
+        p.pval = c.take<float>(nnz + 1);
+        return p;
+    };
+    plan(sizing);
+    void *base = rt::scratch(SCR_STORE_B, sizing.off + 1024);
+    if (!base) return RT_ERR_CUDA;
+    Carver real(base, sizing.off + 1024);
+    auto P = plan(real);
+    // ---- popularity rank -------------------------------------------------------------------------
+    rank_keys_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(d_cptr, I, P.rk);
+    RT_CHECK_LAUNCH();
+    G3_CUB(cub::DeviceRadixSort::SortKeys(d_tmp__, tmp_bytes__, P.rk, P.rks, I, 0, 64, st));
+    rank_scatter_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(P.rks, I, d_orig_of, d_rank_of);
+    RT_CHECK_LAUNCH();
+    for (int p = 0; p <= n_parts; ++p) h_cuts[p] = p == 0 ? 0 : I;
+    if (nnz == 0) { RT_CUDA(cudaStreamSynchronize(st)); return RT_OK; }
+    RT_ARG(d_cidx && d_cval && d_ridx && d_rval, "null pointer");
+    // ---- rank-sorted CSR ---------------------------------------------------------------------------
+    {
+        const unsigned grid = (unsigned)(((int64_t)n_users * 32 + bs - 1) / bs);
+        relabel_keys_kernel<<<grid, bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rank_of, P.keys);
+        RT_CHECK_LAUNCH();
+        const int end_bit = 32 + bits_for_n(n_users);
+        G3_CUB(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys, P.keys2, d_rval, P.pval, (int)nnz, 0, end_bit, st));
+        low32_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(P.keys2, nnz, P.pidx);
+        RT_CHECK_LAUNCH();
+    }
+    {
+        int rc = rt_csr_split(n_users, d_rptr, P.pidx, 0, RW, R, P.hseg, stream);
+        if (rc) return rc;
+    }
+    if (n_parts > 1) RT_CUDA(cudaMemsetAsync(P.cost, 0, sizeof(unsigned long long) * ((size_t)I + 1), st));
+    entry_pos_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(I, nnz, d_rank_of, d_cptr, d_cidx, d_rptr, P.pidx, P.cpos,
+                                                                    n_parts > 1 ? P.cost : nullptr);
+    RT_CHECK_LAUNCH();
+    chunk_count_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(I, d_orig_of, d_cptr, P.n_chunks);
+    RT_CHECK_LAUNCH();
+    RT_CUDA(cudaMemsetAsync(P.n_chunks + I, 0, sizeof(int), st));
+    G3_CUB(cub::DeviceScan::ExclusiveSum(d_tmp__, tmp_bytes__, P.n_chunks, P.chunk_start, I + 1, st));
+    // ---- partition of the rows by exact work -------------------------------------------------------
+    int row_begin = 0, row_end = I;
+    if (n_parts > 1) {
+        G3_CUB(cub::DeviceScan::InclusiveSum(d_tmp__, tmp_bytes__, P.cost, P.cost_s, I, st));
+        std::vector<unsigned long long> cs((size_t)I);
+        RT_CUDA(cudaMemcpyAsync(cs.data(), P.cost_s, sizeof(unsigned long long) * (size_t)I, cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+        const unsigned long long total = cs[I - 1];
+        int pos = 0;
+        for (int p = 1; p < n_parts; ++p) {
+            const unsigned long long want = total / (unsigned long long)n_parts * (unsigned long long)p;
+            while (pos < I && cs[pos] < want) ++pos;
+            h_cuts[p] = pos;
+        }
+        h_cuts[n_parts] = I;
+        row_begin = h_cuts[part];
+        row_end = h_cuts[part + 1];
+    }
+    // ---- lower triangle ----------------------------------------------------------------------------
+    if (row_end > row_begin) {
+        RT_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
+        const size_t smem = sizeof(float) * (size_t)G3_WARPS * G3_SLICE;
+        RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        const int grid = rt::sm_count() * per_sm;
+        gram_lower_kernel<<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, d_orig_of,
+                                                            d_cptr, d_cidx, d_cval, P.cpos, P.hseg, P.pidx, P.pval, d_Gp,
+                                                            ldgp, P.counter);
+        RT_CHECK_LAUNCH();
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                              const int32_t *d_orig_of, float *d_G, int64_t ldg, void *stream) {
+    RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items, "arguments");
+    RT_ARG(d_Gp != d_G, "rt_gram_finish is not in-place");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = (n_items + 31) / 32;
+    gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
+    RT_CHECK_LAUNCH();
+    const size_t row_bytes = sizeof(float) * (size_t)n_items;
+    const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
+    const size_t smem = stage ? row_bytes : 0;
+    RT_CUDA(cudaFuncSetAttribute(gram_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = stage ? (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024)) : 2;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int grid = rt::sm_count() * per_sm;
+    if (grid > n_items) grid = n_items;
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}

@@ -183,6 +183,43 @@ def gram(X: DeviceMatrix, e_begin: int = 0, e_end: Optional[int] = None, out=Non
     return out
 
 
+@dataclass
+class GramLower:
+    """Lower triangle of the Gram matrix in popularity-rank space (output of rt_gram_lower)."""
+    Gp: object        # float32 [I, I] device, rows [cuts[part], cuts[part+1]) filled
+    rank_of: object   # int32 [I]
+    orig_of: object   # int32 [I]
+    cuts: list        # row cut points, len n_parts + 1
+
+
+def gram_lower(X: DeviceMatrix, part: int = 0, n_parts: int = 1) -> GramLower:
+    t = require_cuda()
+    I = X.n_items
+    Gp = t.zeros((I, I), dtype=t.float32, device=dev())
+    rank_of = empty(I, t.int32)
+    orig_of = empty(I, t.int32)
+    cuts = (C.c_int32 * (n_parts + 1))()
+    check(_lib.load().rt_gram_lower(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx),
+                                    ptr(X.rval), X.nnz, int(part), int(n_parts), ptr(Gp), I, ptr(rank_of), ptr(orig_of),
+                                    cuts, stream_ptr()), "rt_gram_lower")
+    return GramLower(Gp, rank_of, orig_of, list(cuts))
+
+
+def gram_finish(L: GramLower, out=None):
+    t = require_cuda()
+    I = L.Gp.shape[0]
+    if out is None:
+        out = t.empty((I, I), dtype=t.float32, device=dev())
+    check(_lib.load().rt_gram_finish(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, stream_ptr()),
+          "rt_gram_finish")
+    return out
+
+
+def gram_full(X: DeviceMatrix, out=None):
+    """Dense symmetric item-item Gram matrix G in item ids (K3, third generation)."""
+    return gram_finish(gram_lower(X), out=out)
+
+
 def gram_cols(X: DeviceMatrix, j_begin: int = 0, j_end: Optional[int] = None, out=None):
     """Gram rows of the target columns [j_begin, j_end) with shared-memory accumulators (rt_gram)."""
     t = require_cuda()

@@ -93,9 +93,23 @@ def item_shard(n_items: int, rank: int, world: int, cptr_host: Optional[np.ndarr
     return cuts[rank], cuts[rank + 1]
 
 
+def exchange_slabs(M, cuts, group=None):
+    """All-gather of unequal row slabs: rank r owns rows [cuts[r], cuts[r+1]) of ``M`` (same cuts on every
+    rank); afterwards every rank holds all rows.  One broadcast per non-empty slab, issued asynchronously."""
+    import torch.distributed as dist
+    works = []
+    for r in range(len(cuts) - 1):
+        a, b = int(cuts[r]), int(cuts[r + 1])
+        if b > a:
+            works.append(dist.broadcast(M[a:b], src=dist.get_global_rank(group, r) if group is not None else r,
+                                        group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
 def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int = 1, group=None,
                 targets=None, want_sel: bool = False):
-    """Gram rows of this rank's item range -> all-gather G (NCCL) -> solve this rank's targets.
+    """Gram row slab of this rank -> all-gather of the slabs (NCCL) -> mirror/unpermute -> solve this rank's targets.
 
     Returns ``(res, (j0, j1))`` where ``res`` holds this rank's columns of W (``SolveResult``).
     With ``world == 1`` this is the single-GPU bulk fit.
@@ -104,22 +118,12 @@ def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int 
     I = X.n_items
     cptr_host = X.cptr.cpu().numpy() if world > 1 else None
     j0, j1 = item_shard(I, rank, world, cptr_host)
-    G = t.zeros((I, I), dtype=t.float32, device=D.dev())
-    if world == 1:
-        D.gram(X, out=G)
-    else:
-        import torch.distributed as dist
-        e0, e1 = int(cptr_host[j0]), int(cptr_host[j1])
-        D.gram(X, e0, e1, out=G)
-        # exchange step: every rank needs G[sel, sel] for arbitrary neighbours -> all-gather rows.
-        # Ranks own different numbers of rows, so gather into the full matrix by broadcasting slabs.
-        cuts = [item_shard(I, r, world, cptr_host) for r in range(world)]
-        works = []
-        for r, (a, b) in enumerate(cuts):
-            if b > a:
-                works.append(dist.broadcast(G[a:b], src=r, group=group, async_op=True))
-        for w in works:
-            w.wait()
+    # K3: this rank's row slab of the rank-space lower triangle (rows balanced by multiply-add count)
+    L = D.gram_lower(X, part=rank, n_parts=world)
+    if world > 1:
+        exchange_slabs(L.Gp, L.cuts, group=group)
+    G = D.gram_finish(L)
+    del L
     if targets is None:
         tg = t.arange(j0, j1, dtype=t.int32, device=D.dev())
     else:

@@ -94,6 +94,37 @@ def test_gram_rows_exact_on_integer_ratings():
     assert np.array_equal(G, G.T)
 
 
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_gram_v3_equals_model_and_shards(shuffle):
+    """Popularity-ranked lower-triangle Gram (rt_gram_lower/finish): exact on integer ratings for any item id
+    order, symmetric, and the row slabs of a 3-way split assemble to the same matrix."""
+    from rtrec_b200 import device as D
+    U, I, N = 3000, 2100, 150000
+    u, i, ts, r = synth_events(U, I, N, seed=4, rating="int")
+    if shuffle:
+        i = np.random.default_rng(0).permutation(I)[i]
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    G_ref = so.gram_model_gram(X)
+    dX = D.DeviceMatrix.from_scipy(X)
+    G = D.gram_full(dX).cpu().numpy()
+    assert np.array_equal(G, G_ref)
+    assert np.array_equal(G, G.T)
+    t = D.torch()
+    parts = [D.gram_lower(dX, part=p, n_parts=3) for p in range(3)]
+    cuts = parts[0].cuts
+    assert cuts[0] == 0 and cuts[-1] == I and all(parts[p].cuts == cuts for p in range(3))
+    for p in (1, 2):
+        parts[0].Gp[cuts[p]:cuts[p + 1]].copy_(parts[p].Gp[cuts[p]:cuts[p + 1]])
+        assert t.equal(parts[p].rank_of, parts[0].rank_of)
+    G3 = D.gram_finish(parts[0]).cpu().numpy()
+    assert np.array_equal(G3, G_ref)
+    # continuous ratings: agreement to fp32 rounding of the differently ordered sums
+    Xc = sp.csc_matrix((np.random.default_rng(1).uniform(0.5, 5.0, len(u)).astype(np.float32), (u, i)), shape=(U, I))
+    Gc = D.gram_full(D.DeviceMatrix.from_scipy(Xc)).cpu().numpy()
+    ref = (Xc.T.astype(np.float64) @ Xc.astype(np.float64)).toarray()
+    assert np.abs(Gc - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
 # ------------------------------------------------------------------------------------------ fit
 @pytest.mark.parametrize("name,cfg", FIT_CASES)
 def test_fit_matches_reference_golden(golden, name, cfg):

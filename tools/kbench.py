@@ -60,6 +60,17 @@ def main():
         res["gram_v1_ms"] = ms1; res["gram_v2_ms"] = ms2
         res["gram_equal"] = bool(torch.equal(G1, G))
         res["gram_maxdiff"] = float((G1 - G).abs().max())
+        box = {}
+        def g3a():
+            box["L"] = D.gram_lower(X); return None
+        ms3a, _ = timeit(g3a)
+        def g3b():
+            D.gram_finish(box["L"], out=G); return None
+        ms3b, _ = timeit(g3b)
+        res["gram_v3_lower_ms"] = ms3a; res["gram_v3_finish_ms"] = ms3b
+        res["gram_v3_equal"] = bool(torch.equal(G1, G))
+        res["gram_v3_maxdiff"] = float((G1 - G).abs().max())
+        box.clear()
         del G1
     else:
         D.gram(X, out=G)
