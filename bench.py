@@ -291,7 +291,8 @@ def run_ours(args):
         import pandas as pd
         df = pd.DataFrame({"user": u, "item": i, "tstamp": ts, "rating": r})
         users_list = list(range(U))
-        h2d = int(u.astype(np.int32).nbytes + i.astype(np.int32).nbytes + ts.nbytes + r.nbytes + 4 * U)
+        # the DataFrame columns are uploaded as they are (int64 ids, f64 timestamps/ratings) + the user list (int32)
+        h2d = int(u.astype(np.int64, copy=False).nbytes + i.astype(np.int64, copy=False).nbytes + ts.nbytes + r.nbytes + 4 * U)
         d2h = int(U * TOP_K * 8 + 4 * U)
         import io
         import contextlib

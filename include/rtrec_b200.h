@@ -73,6 +73,20 @@ int rt_store_fold(const int32_t *d_users, const int32_t *d_items, const double *
                   int32_t *h_max_item, void *stream);
 
 /*
+ * Batch bookkeeping of add_interaction for events that already sit on the device as the int64 / f64
+ * columns a DataFrame holds (interactions.py:92-99 future-timestamp check and max_timestamp,
+ * :113-119 all_item_ids / hot_items / max ids).  rt_events_minmax returns the id ranges (validation,
+ * max_user_id / max_item_id) and the largest timestamp; synchronises.  rt_events_item_stats fills,
+ * per item id < n_items: the number of events with delta > 0 (hot_items frequency, :115-116), the
+ * arrival index of the last such event (-1 if none; LRU order) and a seen flag (all_item_ids).
+ */
+int rt_events_minmax(const int64_t *d_users, const int64_t *d_items, const double *d_ts, int64_t n,
+                     int64_t *h_min_user, int64_t *h_max_user, int64_t *h_min_item, int64_t *h_max_item,
+                     double *h_max_ts, void *stream);
+int rt_events_item_stats(const int64_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
+                         int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream);
+
+/*
  * Build the float32 CSR and CSC interaction matrices from the store (to_csr / to_csc,
  * interactions.py:259-303): x = f32(val * rate^((max_ts - stamp)/86400)), shape
  * (n_users, n_items) = (max_user_id+1, max_item_id+1); explicit zeros are kept.

@@ -14,6 +14,9 @@
 // hand-written.
 #include <cub/cub.cuh>
 
+#include <limits.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace rt {
@@ -160,6 +163,47 @@ __global__ void lookup_kernel(const unsigned long long *keys, const double *vals
     found[q] = f ? 1 : 0;
     val_out[q] = f ? vals[p] : 0.0;
     stamp_out[q] = f ? stamps[p] : 0.0;
+}
+
+// ---- ingest bookkeeping (interactions.py:92-99, 113-119 for a whole batch) ----------------------------
+// out[0..5] = min user, max user, min item, max item (int64), out_ts[0] = max timestamp
+__global__ void events_minmax_kernel(const long long *__restrict__ users, const long long *__restrict__ items,
+                                     const double *__restrict__ ts, int64_t n, long long *__restrict__ out,
+                                     double *__restrict__ out_ts) {
+    long long umin = LLONG_MAX, umax = LLONG_MIN, imin = LLONG_MAX, imax = LLONG_MIN;
+    double tmax = -INFINITY;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const long long u = users[k], i = items[k];
+        umin = min(umin, u); umax = max(umax, u); imin = min(imin, i); imax = max(imax, i);
+        tmax = fmax(tmax, ts[k]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o)); umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o)); imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], umin); atomicMax(&out[1], umax); atomicMin(&out[2], imin); atomicMax(&out[3], imax);
+        // timestamps are non-negative in practice; order-preserving integer max works for any sign
+        long long b = __double_as_longlong(tmax);
+        b = b < 0 ? (b ^ 0x7fffffffffffffffll) : b;
+        atomicMax((long long *)out_ts, b);
+    }
+}
+
+// per item: number of events with delta > 0, arrival index of the last such event, seen flag
+__global__ void events_item_stats_kernel(const long long *__restrict__ items, const double *__restrict__ delta, int64_t n,
+                                         int *__restrict__ count_pos, int *__restrict__ last_pos,
+                                         unsigned char *__restrict__ seen) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long long i = items[k];
+    seen[i] = 1;
+    if (delta[k] > 0.0) {
+        atomicAdd(&count_pos[i], 1);
+        atomicMax(&last_pos[i], (int)k);
+    }
 }
 
 static int bits_for64(long long n) { int b = 1; while ((1ll << b) < n && b < 32) ++b; return b; }
@@ -364,6 +408,50 @@ extern "C" int rt_store_lookup(const uint64_t *d_keys, const double *d_vals, con
     lookup_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
         (const unsigned long long *)d_keys, d_vals, d_stamps, n_pairs, (const unsigned long long *)d_query, n, d_val_out,
         d_stamp_out, d_found);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_events_minmax(const int64_t *d_users, const int64_t *d_items, const double *d_ts, int64_t n,
+                                int64_t *h_min_user, int64_t *h_max_user, int64_t *h_min_item, int64_t *h_max_item,
+                                double *h_max_ts, void *stream) {
+    RT_ARG(n > 0 && d_users && d_items && d_ts, "event arrays");
+    RT_ARG(h_min_user && h_max_user && h_min_item && h_max_item && h_max_ts, "host outputs");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long *d_out = (long long *)rt::scratch(SCR_MISC, 256);
+    if (!d_out) return RT_ERR_CUDA;
+    long long init[5] = {LLONG_MAX, LLONG_MIN, LLONG_MAX, LLONG_MIN, LLONG_MIN};
+    RT_CUDA(cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    int grid = rt::sm_count() * 8;
+    const int64_t want = (n + 255) / 256;
+    if (grid > want) grid = (int)want;
+    events_minmax_kernel<<<grid, 256, 0, st>>>((const long long *)d_users, (const long long *)d_items, d_ts, n, d_out,
+                                              (double *)(d_out + 4));
+    RT_CHECK_LAUNCH();
+    long long host[5];
+    RT_CUDA(cudaMemcpyAsync(host, d_out, sizeof(host), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    *h_min_user = host[0]; *h_max_user = host[1]; *h_min_item = host[2]; *h_max_item = host[3];
+    long long b = host[4];
+    b = b < 0 ? (b ^ 0x7fffffffffffffffll) : b;
+    double t;
+    memcpy(&t, &b, sizeof(t));
+    *h_max_ts = t;
+    return RT_OK;
+}
+
+extern "C" int rt_events_item_stats(const int64_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
+                                    int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream) {
+    RT_ARG(n >= 0 && n < (1ll << 31) && n_items > 0, "sizes");
+    RT_ARG(d_count_pos && d_last_pos && d_seen, "outputs");
+    cudaStream_t st = (cudaStream_t)stream;
+    RT_CUDA(cudaMemsetAsync(d_count_pos, 0, sizeof(int) * (size_t)n_items, st));
+    RT_CUDA(cudaMemsetAsync(d_last_pos, 0xff, sizeof(int) * (size_t)n_items, st));  // -1
+    RT_CUDA(cudaMemsetAsync(d_seen, 0, (size_t)n_items, st));
+    if (n == 0) return RT_OK;
+    RT_ARG(d_items && d_delta, "event arrays");
+    events_item_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long *)d_items, d_delta, n, d_count_pos,
+                                                                         d_last_pos, d_seen);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -151,6 +151,12 @@ class BaseModel(ABC):
         """base.py:188-269."""
         cold_slots, hot_slots, hot_ids = [], [], []
         cold_ids: List[Optional[int]] = []
+        if self.user_ids.pass_through and len(users) >= 1024:
+            # integer pass-through ids (identifiers.py:69-72): resolve the whole list at once
+            arr = np.asarray(users)
+            if arr.dtype.kind in "iu" and arr.ndim == 1 and (arr.min() >= 0) and (arr.max() <= self.interactions.max_user_id):
+                hot_ids = arr
+                users = ()
         for slot, user in enumerate(users):
             uid = self._resolve_user(user)
             if uid is None:

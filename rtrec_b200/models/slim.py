@@ -78,7 +78,9 @@ class SLIM(BaseModel):
         ids, _, cnt = self.model.recommend_batch_device(np.asarray(user_ids, dtype=np.int64), X, candidate_item_ids,
                                                         top_k, filter_interacted, dense_output)
         rows = ids.tolist()
-        return [row[:c] for row, c in zip(rows, cnt.tolist())]
+        if len(cnt) and int(cnt.min()) == ids.shape[1]:
+            return rows  # every list is full: nothing to trim
+        return [row if c == len(row) else row[:c] for row, c in zip(rows, cnt.tolist())]
 
     def _similar_items(self, query_item_id: int, query_item_tags: Optional[List[str]] = None, top_k: int = 10) -> List[Tuple[int, float]]:
         """slim.py:106-115."""

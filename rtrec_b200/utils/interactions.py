@@ -25,6 +25,7 @@ from .lru import LRUFreqSet
 
 _INT32_MAX = 2**31 - 1
 _FLUSH_AT = 1 << 22  # pending events before an automatic fold
+_DEVICE_INGEST_AT = 1 << 16  # batch size from which the bookkeeping runs on the device
 
 
 class UserItemInteractions:
@@ -118,6 +119,8 @@ class UserItemInteractions:
             return
         if not (len(i) == n and len(ts) == n and len(d) == n):
             raise ValueError("event arrays must have equal length")
+        if n >= _DEVICE_INGEST_AT and self._ingest_on_device(u, i, ts, d, bool(upsert)):
+            return
         if u.min() < 0 or i.min() < 0 or u.max() > _INT32_MAX or i.max() > _INT32_MAX:
             raise ValueError("ids outside [0, 2^31): the device store indexes with int32")
         self._warn_future(float(ts.max()))
@@ -140,6 +143,46 @@ class UserItemInteractions:
         self._touch()
         if self._pend_n >= _FLUSH_AT:
             self._flush()
+
+    def _ingest_on_device(self, u: np.ndarray, i: np.ndarray, ts: np.ndarray, d: np.ndarray, upsert: bool) -> bool:
+        """Large batches: upload the four columns as they are and let the device produce the batch
+        bookkeeping (id ranges, max timestamp, per-item hot counts / last touch / seen flags); the
+        host only walks the distinct items.  Returns False (nothing changed) when the item ids are too
+        sparse for dense per-item counters or an LRU eviction could occur, so that the host path runs."""
+        t = D.require_cuda()
+        lib = _lib.load()
+        du, di, dts, dd = D.to_dev(u), D.to_dev(i), D.to_dev(ts), D.to_dev(d)
+        n = len(u)
+        lo_u, hi_u, lo_i, hi_i, mx_ts = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
+        _lib.check(lib.rt_events_minmax(D.ptr(du), D.ptr(di), D.ptr(dts), n, C.byref(lo_u), C.byref(hi_u), C.byref(lo_i),
+                                        C.byref(hi_i), C.byref(mx_ts), D.stream_ptr()), "rt_events_minmax")
+        if lo_u.value < 0 or lo_i.value < 0 or hi_u.value > _INT32_MAX or hi_i.value > _INT32_MAX:
+            raise ValueError("ids outside [0, 2^31): the device store indexes with int32")
+        imax = int(hi_i.value)
+        if imax >= 8 * n + (1 << 20):
+            return False
+        cnt = D.empty(imax + 1, t.int32); last = D.empty(imax + 1, t.int32); seen = D.empty(imax + 1, t.uint8)
+        _lib.check(lib.rt_events_item_stats(D.ptr(di), D.ptr(dd), n, imax + 1, D.ptr(cnt), D.ptr(last), D.ptr(seen),
+                                            D.stream_ptr()), "rt_events_item_stats")
+        cnt_h, last_h, seen_h = cnt.cpu().numpy(), last.cpu().numpy(), seen.cpu().numpy()
+        hot = np.flatnonzero(cnt_h)
+        if not self.hot_items.add_counts(hot, cnt_h[hot], last_h[hot]):
+            return False
+        self._warn_future(float(mx_ts.value))
+        self.max_timestamp = max(self.max_timestamp, float(mx_ts.value) + 1.0)
+        if self._pend_upsert is not None and self._pend_upsert != upsert:
+            self._flush()
+        self._pend_upsert = upsert
+        self._seal_scalars()
+        self._pend.append((du.to(t.int32), di.to(t.int32), dts, dd))
+        self._pend_n += n
+        self.all_item_ids.update(np.flatnonzero(seen_h).tolist())
+        self.max_user_id = max(self.max_user_id, int(hi_u.value))
+        self.max_item_id = max(self.max_item_id, imax)
+        self._touch()
+        if self._pend_n >= _FLUSH_AT:
+            self._flush()
+        return True
 
     def _touch(self) -> None:
         self.version += 1
@@ -170,15 +213,14 @@ class UserItemInteractions:
             return
         t = D.require_cuda()
         lib = _lib.load()
-        if len(self._pend) == 1:
-            u, i, ts, d = self._pend[0]
-        else:
-            u = np.concatenate([p[0] for p in self._pend]); i = np.concatenate([p[1] for p in self._pend])
-            ts = np.concatenate([p[2] for p in self._pend]); d = np.concatenate([p[3] for p in self._pend])
+        cols = []
+        for c in range(4):
+            parts = [p[c] if not isinstance(p[c], np.ndarray) else D.to_dev(p[c]) for p in self._pend]
+            cols.append(parts[0] if len(parts) == 1 else t.cat(parts))
+        du, di, dts, dd = cols
         upsert = bool(self._pend_upsert)
         self._pend, self._pend_n, self._pend_upsert = [], 0, None
-        n = len(u)
-        du, di, dts, dd = D.to_dev(u), D.to_dev(i), D.to_dev(ts), D.to_dev(d)
+        n = int(du.numel())
         cap = self._n_pairs + n
         ok = D.empty(cap, t.int64); ov = D.empty(cap, t.float64); os_ = D.empty(cap, t.float64)
         n_out, mts, mu, mi = C.c_int64(0), C.c_double(0), C.c_int32(0), C.c_int32(0)

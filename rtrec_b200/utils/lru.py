@@ -68,16 +68,26 @@ class LRUFreqSet(MutableSet):
             uniq, inv, counts = np.unique(values, return_inverse=True, return_counts=True)
             last = np.full(len(uniq), -1, dtype=np.int64)
             last[inv] = np.arange(n)  # later occurrences overwrite earlier ones
-        n_fresh = sum(1 for k in uniq.tolist() if k not in self.data)
-        if len(self.data) + n_fresh > self.capacity:
+        if not self.add_counts(uniq, counts, last):
             # an eviction can happen somewhere inside the batch: replay it event by event
             for v in values.tolist():
                 self.add(v)
-            return
+
+    def add_counts(self, uniq: np.ndarray, counts: np.ndarray, last: np.ndarray) -> bool:
+        """Apply a batch summarised as (distinct key, number of adds, arrival index of its last add).
+        Same end state as the event-by-event loop provided no eviction can occur; returns False
+        (and changes nothing) when one could, so the caller replays the events one by one."""
+        keys = uniq.tolist()
+        n_fresh = sum(1 for k in keys if k not in self.data)
+        if len(self.data) + n_fresh > self.capacity:
+            return False
         # no eviction: counters add up, touched keys move to the MRU end ordered by last touch
+        cnt = counts.tolist()
+        data = self.data
         for j in np.argsort(last, kind="stable").tolist():
-            key = uniq[j].item()
-            self.data[key] = self.data.pop(key, 0) + int(counts[j])
+            key = keys[j]
+            data[key] = data.pop(key, 0) + cnt[j]
+        return True
 
     # -- queries -----------------------------------------------------------------------------
     def get_freq_items(self, n: Optional[int] = None, exclude_items: List[Any] = []) -> Iterator[Any]:
