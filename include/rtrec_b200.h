@@ -85,6 +85,25 @@ int rt_events_minmax(const int64_t *d_users, const int64_t *d_items, const doubl
                      double *h_max_ts, void *stream);
 int rt_events_item_stats(const int64_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
                          int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream);
+/* same for int32 item ids (what rt_upload_events leaves on the device) */
+int rt_events_item_stats32(const int32_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
+                           int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream);
+
+/*
+ * Host -> device upload of one batch of events held as four HOST columns in pageable memory (the
+ * columns of the DataFrame that recommender.py:203-223 would otherwise walk row by row): int64 user
+ * and item ids are narrowed to int32 on the way, timestamps / ratings stay float64.  n_threads host
+ * threads (0 = choose) each convert a chunk into a pinned staging slot owned by the library and
+ * issue the DMA on their own copy stream, so conversion, staging and PCIe transfers overlap.
+ * Also returns the id ranges and the largest timestamp of the batch (interactions.py:92-99,
+ * 118-119); ids outside [0, 2^31) are reported through these ranges and must be rejected by the
+ * caller (the device copies are then meaningless).  Waits for `stream` first (the destinations may
+ * come from a stream-ordered allocator) and returns when the data is resident.
+ */
+int rt_upload_events(const int64_t *h_users, const int64_t *h_items, const double *h_ts,
+                     const double *h_delta, int64_t n, int32_t *d_users, int32_t *d_items, double *d_ts,
+                     double *d_delta, int64_t *h_min_user, int64_t *h_max_user, int64_t *h_min_item,
+                     int64_t *h_max_item, double *h_max_ts, int32_t n_threads, void *stream);
 
 /*
  * Build the float32 CSR and CSC interaction matrices from the store (to_csr / to_csc,

@@ -53,6 +53,9 @@ PROTOTYPES = {
     "rt_events_minmax": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64),
                                    C.POINTER(_F64), _P]),
     "rt_events_item_stats": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "rt_events_item_stats32": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "rt_upload_events": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64),
+                                   C.POINTER(_I64), C.POINTER(_F64), _I32, _P]),
     "rt_store_build": (C.c_int, [_P, _P, _P, _I64, _F64, _F64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P,
                                  C.POINTER(_I64), C.POINTER(C.c_int), _P]),
     "rt_store_lookup": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),

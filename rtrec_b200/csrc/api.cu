@@ -92,8 +92,10 @@ extern "C" int rt_set_option(const char *name, int32_t value) {
     rt::set_error("rt_set_option: unknown option '%s'", name);
     return RT_ERR_ARG;
 }
+namespace rt { void upload_release(); }
 extern "C" void rt_release_scratch(void) {
     cudaDeviceSynchronize();
+    rt::upload_release();
     for (int i = 0; i < rt::SCR_SLOTS; ++i) {
         if (rt::g_scr[i]) cudaFree(rt::g_scr[i]);
         rt::g_scr[i] = nullptr;

@@ -193,12 +193,13 @@ __global__ void events_minmax_kernel(const long long *__restrict__ users, const 
 }
 
 // per item: number of events with delta > 0, arrival index of the last such event, seen flag
-__global__ void events_item_stats_kernel(const long long *__restrict__ items, const double *__restrict__ delta, int64_t n,
+template <typename IdT>
+__global__ void events_item_stats_kernel(const IdT *__restrict__ items, const double *__restrict__ delta, int64_t n,
                                          int *__restrict__ count_pos, int *__restrict__ last_pos,
                                          unsigned char *__restrict__ seen) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const long long i = items[k];
+    const long long i = (long long)items[k];
     seen[i] = 1;
     if (delta[k] > 0.0) {
         atomicAdd(&count_pos[i], 1);
@@ -440,8 +441,8 @@ extern "C" int rt_events_minmax(const int64_t *d_users, const int64_t *d_items, 
     return RT_OK;
 }
 
-extern "C" int rt_events_item_stats(const int64_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
-                                    int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream) {
+static int events_item_stats_impl(const void *d_items, int wide, const double *d_delta, int64_t n, int32_t n_items,
+                                  int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream) {
     RT_ARG(n >= 0 && n < (1ll << 31) && n_items > 0, "sizes");
     RT_ARG(d_count_pos && d_last_pos && d_seen, "outputs");
     cudaStream_t st = (cudaStream_t)stream;
@@ -450,8 +451,19 @@ extern "C" int rt_events_item_stats(const int64_t *d_items, const double *d_delt
     RT_CUDA(cudaMemsetAsync(d_seen, 0, (size_t)n_items, st));
     if (n == 0) return RT_OK;
     RT_ARG(d_items && d_delta, "event arrays");
-    events_item_stats_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const long long *)d_items, d_delta, n, d_count_pos,
-                                                                         d_last_pos, d_seen);
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (wide) events_item_stats_kernel<long long><<<grid, 256, 0, st>>>((const long long *)d_items, d_delta, n, d_count_pos, d_last_pos, d_seen);
+    else events_item_stats_kernel<int><<<grid, 256, 0, st>>>((const int *)d_items, d_delta, n, d_count_pos, d_last_pos, d_seen);
     RT_CHECK_LAUNCH();
     return RT_OK;
+}
+
+extern "C" int rt_events_item_stats(const int64_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
+                                    int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream) {
+    return events_item_stats_impl(d_items, 1, d_delta, n, n_items, d_count_pos, d_last_pos, d_seen, stream);
+}
+
+extern "C" int rt_events_item_stats32(const int32_t *d_items, const double *d_delta, int64_t n, int32_t n_items,
+                                      int32_t *d_count_pos, int32_t *d_last_pos, uint8_t *d_seen, void *stream) {
+    return events_item_stats_impl(d_items, 0, d_delta, n, n_items, d_count_pos, d_last_pos, d_seen, stream);
 }

@@ -4,7 +4,7 @@ Same constructor config, methods and error behaviour as the reference operator
 (/root/reference/rtrec/models/internal/slim_elastic.py:156-857); the arithmetic runs in the
 hand-written kernels of ``librtrec_b200.so``:
 
-    fit / fit_in_parallel / partial_fit_items  ->  rt_gram_rows (K3) + rt_slim_solve (K4) + rt_w_merge (K5)
+    fit / fit_in_parallel / partial_fit_items  ->  rt_gram_lower/finish (K3) + rt_slim_solve (K4) + rt_w_merge (K5)
     recommend / recommend_batch                ->  rt_slim_recommend[_candidates] (K6)
     similar_items                              ->  rt_slim_similar (K8)
 
@@ -73,12 +73,6 @@ class SLIMElastic:
             self._W = D.DeviceW.from_scipy(self._W_host)
         return self._W
 
-    def __getstate__(self):
-        st = dict(self.__dict__)
-        st["_W_host"] = self.item_similarity
-        st["_W"] = None
-        return st
-
     # ------------------------------------------------------------------ helpers
     def _check_optim(self) -> None:
         if self.optim_name == "cd":
@@ -109,7 +103,7 @@ class SLIMElastic:
         cfg = self._config(X)
         n_items = X.n_items
         tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
-        G = D.gram(X)
+        G = D.gram_full(X) if X.nnz > 0 else D.gram(X)
         sel_dev = None
         if sel_in is not None and cfg.nn > 0:
             sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))
@@ -225,6 +219,53 @@ class SLIMElastic:
         mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
         ids, scores, cnt = D.recommend(X, users, W, kk, filter_interacted, mode)
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
+
+    _LIST_CHUNK = 16384  # users per launch when the result is wanted as Python lists
+
+    def recommend_lists(self, user_ids: np.ndarray, X: D.DeviceMatrix, top_k: int = 10, filter_interacted: bool = True,
+                        dense_output: bool = True) -> List[List[int]]:
+        """``recommend_batch`` without candidates for many users, as Python lists.  The users are scored in
+        chunks; every chunk's kernel and its device->host copy (into a pinned buffer) are queued up front, and
+        the host turns chunk c into lists while the GPU is still scoring chunk c+1."""
+        W = self._require_fitted("batch_recommend")
+        t = D.require_cuda()
+        if X.n_items != W.n_items:
+            raise ValueError(f"dimension mismatch: interaction matrix has {X.n_items} items, W has {W.n_items}")
+        Q = len(user_ids)
+        k = max(1, min(int(top_k), 128))
+        mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
+        users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
+        pin = getattr(self, "_pin", None)
+        if pin is None or pin[0].numel() < Q * k or pin[1].numel() < Q:
+            pin = (t.empty(Q * k, dtype=t.int32, pin_memory=True), t.empty(Q, dtype=t.int32, pin_memory=True))
+            self._pin = pin
+        h_ids, h_cnt = pin[0][:Q * k].view(Q, k), pin[1][:Q]
+        pending = []
+        for a in range(0, Q, self._LIST_CHUNK):
+            b = min(a + self._LIST_CHUNK, Q)
+            ids, _, cnt = D.recommend(X, users[a:b], W, k, filter_interacted, mode)
+            h_ids[a:b].copy_(ids, non_blocking=True)
+            h_cnt[a:b].copy_(cnt, non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record()
+            pending.append((a, b, ev))
+        out: List[List[int]] = []
+        ids_np, cnt_np = h_ids.numpy(), h_cnt.numpy()
+        for a, b, ev in pending:
+            ev.synchronize()
+            rows = ids_np[a:b].tolist()
+            c = cnt_np[a:b]
+            if int(c.min()) < k:
+                rows = [row if n == k else row[:n] for row, n in zip(rows, c.tolist())]
+            out.extend(rows)
+        return out
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_W_host"] = self.item_similarity
+        st["_W"] = None
+        st.pop("_pin", None)
+        return st
 
     def similar_items(self, item_id: int, top_k: int = 10, ret_ndarrays: bool = False):
         """slim_elastic.py:820-857."""

@@ -75,6 +75,8 @@ class SLIM(BaseModel):
             return []
         X = self.interactions.device_matrix()
         dense_output = not self.item_ids.pass_through
+        if candidate_item_ids is None:
+            return self.model.recommend_lists(np.asarray(user_ids, dtype=np.int64), X, top_k, filter_interacted, dense_output)
         ids, _, cnt = self.model.recommend_batch_device(np.asarray(user_ids, dtype=np.int64), X, candidate_item_ids,
                                                         top_k, filter_interacted, dense_output)
         rows = ids.tolist()

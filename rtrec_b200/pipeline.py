@@ -74,22 +74,37 @@ def build_matrix(state: StoreState, *, decay_rate: Optional[float], max_ts: Opti
 
 # ------------------------------------------------------------------------------------------ sharding
 def item_shard(n_items: int, rank: int, world: int, cptr_host: Optional[np.ndarray] = None) -> Tuple[int, int]:
-    """Contiguous item range [j0, j1) owned by ``rank``.  With the CSC column pointer given, the cut
-    points balance the Gram work (entries per column weighted by mean row length is close to
-    balancing stored entries); otherwise equal item counts."""
+    """Contiguous item range [j0, j1) owned by ``rank``: equal column counts.  One ElasticNet solve costs
+    about the same for every target (nn candidates each), and the scoring work of a shard is the number of
+    W entries in its columns (<= nn per column), so the count -- not the stored entries of X, which would
+    hand the popular head to one rank and nearly every column to the last -- is what balances the ranks.
+    ``cptr_host`` is accepted for compatibility and ignored."""
     if world <= 1:
         return 0, n_items
-    if cptr_host is None:
-        cuts = [(n_items * r) // world for r in range(world + 1)]
-    else:
-        nnz = int(cptr_host[-1])
-        cuts = [0]
-        for r in range(1, world):
-            cuts.append(int(np.searchsorted(cptr_host, (nnz * r) // world, side="left")))
-        cuts.append(n_items)
-        cuts = [min(max(c, 0), n_items) for c in cuts]
-        for r in range(1, world + 1):
-            cuts[r] = max(cuts[r], cuts[r - 1])
+    return (n_items * rank) // world, (n_items * (rank + 1)) // world
+
+
+def query_cuts(rptr, users, world: int) -> list:
+    """Cut points (len world + 1) of the query list, balanced by the stored entries of the queried rows
+    (the scoring work of a user grows with its row length).  Computed from replicated data, so every rank
+    derives the same list."""
+    t = D.torch()
+    Q = int(users.numel())
+    if world <= 1 or Q == 0:
+        return [0] + [Q] * max(world, 1)
+    ul = users.long()
+    work = (rptr[ul + 1] - rptr[ul]).long() + 8  # + fixed per-user cost
+    csum = t.cumsum(work, 0)
+    frac = t.arange(1, world, dtype=t.int64, device=csum.device)
+    want = (csum[-1] * frac) // world
+    cuts = [0] + t.searchsorted(csum, want).tolist() + [Q]
+    for r in range(1, world + 1):
+        cuts[r] = min(max(cuts[r], cuts[r - 1]), Q)
+    return cuts
+
+
+def query_shard(rptr, users, rank: int, world: int) -> Tuple[int, int]:
+    cuts = query_cuts(rptr, users, world)
     return cuts[rank], cuts[rank + 1]
 
 
@@ -116,8 +131,7 @@ def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int 
     """
     t = D.require_cuda()
     I = X.n_items
-    cptr_host = X.cptr.cpu().numpy() if world > 1 else None
-    j0, j1 = item_shard(I, rank, world, cptr_host)
+    j0, j1 = item_shard(I, rank, world)
     # K3: this rank's row slab of the rank-space lower triangle (rows balanced by multiply-add count)
     L = D.gram_lower(X, part=rank, n_parts=world)
     if world > 1:
@@ -133,9 +147,55 @@ def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int 
     return res, (j0, j1)
 
 
+def all_gather_ragged(x, counts: list, group=None):
+    """All-gather of 1-D tensors of unequal length: rank r contributes ``x[:counts[r]]`` (``counts`` is known
+    to every rank); returns the list of per-rank pieces.  One padded ``all_gather_into_tensor``."""
+    import torch.distributed as dist
+    t = D.torch()
+    world = len(counts)
+    rank = dist.get_rank(group)
+    n_max = max(max(counts), 1)
+    buf = t.zeros(n_max, dtype=x.dtype, device=x.device)
+    if counts[rank]:
+        buf[:counts[rank]] = x[:counts[rank]]
+    out = t.empty((world, n_max), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out.view(-1), buf, group=group)
+    return [out[r, :counts[r]] for r in range(world)]
+
+
+def gather_solve_results(res: D.SolveResult, world: int, group=None) -> D.SolveResult:
+    """All-gather (NCCL) of the per-rank solver outputs: every rank ends up with the (target, rows, values)
+    triples of all targets, ready for ``w_merge``."""
+    if world <= 1:
+        return res
+    import torch.distributed as dist
+    t = D.torch()
+    dev = res.targets.device
+    T = int(res.targets.numel())
+    meta = t.tensor([T, int(res.n_pairs)], dtype=t.int64, device=dev)
+    metas = t.empty((world, 2), dtype=t.int64, device=dev)
+    dist.all_gather_into_tensor(metas.view(-1), meta, group=group)
+    metas = metas.cpu().tolist()
+    Ts = [int(m[0]) for m in metas]
+    Ps = [int(m[1]) for m in metas]
+    g_t = all_gather_ragged(res.targets, Ts, group)
+    g_off = all_gather_ragged(res.off, Ts, group)
+    g_cnt = all_gather_ragged(res.cnt, Ts, group)
+    g_rows = all_gather_ragged(res.rows, Ps, group)
+    g_vals = all_gather_ragged(res.vals, Ps, group)
+    g_stats = all_gather_ragged(res.stats.reshape(-1), [4 * x for x in Ts], group)
+    base, off = 0, []
+    for r in range(world):
+        off.append(g_off[r] + base)
+        base += Ps[r]
+    return D.SolveResult(t.cat(g_t), t.cat(off), t.cat(g_cnt), t.cat(g_rows), t.cat(g_vals), None,
+                         t.cat(g_stats).view(-1, 4), res.rows_sorted, base)
+
+
 def recommend_sharded(X: D.DeviceMatrix, users, W_shard: D.DeviceW, j_range: Tuple[int, int], k: int,
                       filter_interacted: bool, mode: int, *, world: int = 1, group=None):
-    """K6 on this rank's item columns, all-gather of the per-rank (ids, scores) lists, K7 merge."""
+    """Item-partitioned scoring: K6 on this rank's item columns for every user, all-gather of the per-rank
+    (ids, scores) lists, K7 merge.  ``W_shard`` needs only the columns ``j_range`` of W."""
     t = D.require_cuda()
     ids, scores, cnt = D.recommend(X, users, W_shard, k, filter_interacted, mode, j_range[0], j_range[1])
     if world == 1:
@@ -147,3 +207,31 @@ def recommend_sharded(X: D.DeviceMatrix, users, W_shard: D.DeviceW, j_range: Tup
     dist.all_gather_into_tensor(all_ids.view(-1), ids.contiguous().view(-1), group=group)
     dist.all_gather_into_tensor(all_sc.view(-1), scores.contiguous().view(-1), group=group)
     return D.topk_merge(all_ids, all_sc, world, Q, k)
+
+
+def recommend_query_sharded(X: D.DeviceMatrix, users, W: D.DeviceW, k: int, filter_interacted: bool, mode: int, *,
+                            rank: int = 0, world: int = 1, group=None):
+    """Query-partitioned scoring: every rank holds all of W (a few MB), scores its slice of the query list
+    against every item column (no merge step), and the finished top-k lists are all-gathered so that every
+    rank returns the lists of all users."""
+    t = D.require_cuda()
+    if world == 1:
+        return D.recommend(X, users, W, k, filter_interacted, mode)
+    import torch.distributed as dist
+    Q = int(users.numel())
+    cuts = query_cuts(X.rptr, users, world)
+    bounds = [(cuts[r], cuts[r + 1]) for r in range(world)]
+    q0, q1 = bounds[rank]
+    ids, scores, cnt = D.recommend(X, users[q0:q1], W, k, filter_interacted, mode)
+    m = max(b - a for a, b in bounds)
+    pack = t.zeros((max(m, 1), 2 * k + 1), dtype=t.int32, device=D.dev())
+    n = q1 - q0
+    if n:
+        pack[:n, :k] = ids
+        pack[:n, k:2 * k] = scores.view(t.int32)
+        pack[:n, 2 * k] = cnt
+    out = t.empty((world, max(m, 1), 2 * k + 1), dtype=t.int32, device=D.dev())
+    dist.all_gather_into_tensor(out.view(-1), pack.view(-1), group=group)
+    parts = [out[r, :b - a] for r, (a, b) in enumerate(bounds)]
+    full = t.cat(parts, 0)
+    return full[:, :k].contiguous(), full[:, k:2 * k].contiguous().view(t.float32), full[:, 2 * k].contiguous()

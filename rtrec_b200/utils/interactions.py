@@ -147,37 +147,53 @@ class UserItemInteractions:
     def _ingest_on_device(self, u: np.ndarray, i: np.ndarray, ts: np.ndarray, d: np.ndarray, upsert: bool) -> bool:
         """Large batches: upload the four columns as they are and let the device produce the batch
         bookkeeping (id ranges, max timestamp, per-item hot counts / last touch / seen flags); the
-        host only walks the distinct items.  Returns False (nothing changed) when the item ids are too
-        sparse for dense per-item counters or an LRU eviction could occur, so that the host path runs."""
+        host only walks the distinct items.  When the item ids are too sparse for dense per-item counters, or an
+        LRU eviction could occur inside the batch, that part of the bookkeeping is replayed on the host."""
         t = D.require_cuda()
         lib = _lib.load()
-        du, di, dts, dd = D.to_dev(u), D.to_dev(i), D.to_dev(ts), D.to_dev(d)
         n = len(u)
+        # pageable host columns -> device through the library's threaded staging pipeline (ids narrowed to int32)
+        du, di = D.empty(n, t.int32), D.empty(n, t.int32)
+        dts, dd = D.empty(n, t.float64), D.empty(n, t.float64)
         lo_u, hi_u, lo_i, hi_i, mx_ts = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
-        _lib.check(lib.rt_events_minmax(D.ptr(du), D.ptr(di), D.ptr(dts), n, C.byref(lo_u), C.byref(hi_u), C.byref(lo_i),
-                                        C.byref(hi_i), C.byref(mx_ts), D.stream_ptr()), "rt_events_minmax")
+        _lib.check(lib.rt_upload_events(u.ctypes.data, i.ctypes.data, ts.ctypes.data, d.ctypes.data, n, D.ptr(du), D.ptr(di),
+                                        D.ptr(dts), D.ptr(dd), C.byref(lo_u), C.byref(hi_u), C.byref(lo_i), C.byref(hi_i),
+                                        C.byref(mx_ts), 0, D.stream_ptr()), "rt_upload_events")
         if lo_u.value < 0 or lo_i.value < 0 or hi_u.value > _INT32_MAX or hi_i.value > _INT32_MAX:
             raise ValueError("ids outside [0, 2^31): the device store indexes with int32")
         imax = int(hi_i.value)
         if imax >= 8 * n + (1 << 20):
-            return False
+            return self._queue_device_batch(du, di, dts, dd, upsert, int(hi_u.value), imax, float(mx_ts.value), i, d)
         cnt = D.empty(imax + 1, t.int32); last = D.empty(imax + 1, t.int32); seen = D.empty(imax + 1, t.uint8)
-        _lib.check(lib.rt_events_item_stats(D.ptr(di), D.ptr(dd), n, imax + 1, D.ptr(cnt), D.ptr(last), D.ptr(seen),
-                                            D.stream_ptr()), "rt_events_item_stats")
+        _lib.check(lib.rt_events_item_stats32(D.ptr(di), D.ptr(dd), n, imax + 1, D.ptr(cnt), D.ptr(last), D.ptr(seen),
+                                              D.stream_ptr()), "rt_events_item_stats32")
         cnt_h, last_h, seen_h = cnt.cpu().numpy(), last.cpu().numpy(), seen.cpu().numpy()
         hot = np.flatnonzero(cnt_h)
         if not self.hot_items.add_counts(hot, cnt_h[hot], last_h[hot]):
-            return False
-        self._warn_future(float(mx_ts.value))
-        self.max_timestamp = max(self.max_timestamp, float(mx_ts.value) + 1.0)
+            # an LRU eviction can happen inside the batch: replay the hot-item updates event by event on the host
+            pos = d > 0
+            self.hot_items.add_batch(i[pos] if not pos.all() else i)
+        self.all_item_ids.update(np.flatnonzero(seen_h).tolist())
+        return self._queue_device_batch(du, di, dts, dd, upsert, int(hi_u.value), imax, float(mx_ts.value), None, None)
+
+    def _queue_device_batch(self, du, di, dts, dd, upsert: bool, umax: int, imax: int, ts_max: float,
+                            host_items: Optional[np.ndarray], host_delta: Optional[np.ndarray]) -> bool:
+        """Common tail of the device ingest: queue the resident columns for the next fold and update the
+        exact host bookkeeping.  ``host_items`` given = item ids too sparse for dense device counters:
+        all_item_ids / hot_items are then updated from the host arrays."""
+        if host_items is not None:
+            self.all_item_ids.update(np.unique(host_items).tolist())
+            pos = host_delta > 0
+            self.hot_items.add_batch(host_items[pos] if not pos.all() else host_items)
+        self._warn_future(ts_max)
+        self.max_timestamp = max(self.max_timestamp, ts_max + 1.0)
         if self._pend_upsert is not None and self._pend_upsert != upsert:
             self._flush()
         self._pend_upsert = upsert
         self._seal_scalars()
-        self._pend.append((du.to(t.int32), di.to(t.int32), dts, dd))
-        self._pend_n += n
-        self.all_item_ids.update(np.flatnonzero(seen_h).tolist())
-        self.max_user_id = max(self.max_user_id, int(hi_u.value))
+        self._pend.append((du, di, dts, dd))
+        self._pend_n += int(du.numel())
+        self.max_user_id = max(self.max_user_id, umax)
         self.max_item_id = max(self.max_item_id, imax)
         self._touch()
         if self._pend_n >= _FLUSH_AT:

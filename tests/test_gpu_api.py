@@ -8,6 +8,8 @@ import numpy as np
 import pandas as pd
 import pytest
 
+from oracle.synth import synth_events
+
 pytestmark = pytest.mark.gpu
 
 
@@ -150,3 +152,77 @@ def test_recommender_facade_end_to_end(golden):
     assert 0.0 <= scores["ndcg"] <= 1.0
     sims = rec.similar_items([0, 1], top_k=3, ret_scores=True)
     assert len(sims) == 2
+
+
+def test_upload_events_threaded_staging():
+    """rt_upload_events: pageable int64/f64 columns -> int32/f64 device columns, exact, any chunk count / thread
+    count, id ranges and max timestamp reduced on the way."""
+    import ctypes as C
+    import torch
+    from rtrec_b200 import _lib, device as D
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    for n, threads in [(1, 0), (1000, 1), ((1 << 18) + 17, 3), (3 * (1 << 18) + 5, 0)]:
+        u = rng.integers(0, 2**31 - 1, n).astype(np.int64)
+        i = rng.integers(0, 50_000, n).astype(np.int64)
+        ts = rng.uniform(1e9, 2e9, n)
+        d = rng.normal(size=n)
+        du, di = D.empty(n, torch.int32), D.empty(n, torch.int32)
+        dts, dd = D.empty(n, torch.float64), D.empty(n, torch.float64)
+        lo_u, hi_u, lo_i, hi_i, mx = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
+        _lib.check(lib.rt_upload_events(u.ctypes.data, i.ctypes.data, ts.ctypes.data, d.ctypes.data, n, D.ptr(du), D.ptr(di),
+                                        D.ptr(dts), D.ptr(dd), C.byref(lo_u), C.byref(hi_u), C.byref(lo_i), C.byref(hi_i),
+                                        C.byref(mx), threads, D.stream_ptr()))
+        assert np.array_equal(du.cpu().numpy(), u.astype(np.int32))
+        assert np.array_equal(di.cpu().numpy(), i.astype(np.int32))
+        assert np.array_equal(dts.cpu().numpy(), ts) and np.array_equal(dd.cpu().numpy(), d)
+        assert (lo_u.value, hi_u.value, lo_i.value, hi_i.value) == (u.min(), u.max(), i.min(), i.max())
+        assert mx.value == ts.max()
+
+
+def test_batch_ingest_device_path_equals_event_loop():
+    """A batch large enough for the device ingest path leaves exactly the state the per-event path leaves
+    (store matrix, maxima, all_item_ids, hot items), and rejects ids outside int32."""
+    from rtrec_b200.utils import interactions as inter
+    n = inter._DEVICE_INGEST_AT + 1000
+    u, i, ts, r = synth_events(3000, 500, n, seed=11, rating="int", dup_frac=0.2)
+    r = r - 2.0  # some non-positive deltas (hot_items counts only delta > 0)
+    a = inter.UserItemInteractions(decay_in_days=30)
+    a.add_interactions_batch(u, i, ts, r)
+    b = inter.UserItemInteractions(decay_in_days=30)
+    step = 9973  # below the device threshold: host bookkeeping path
+    for s in range(0, n, step):
+        b.add_interactions_batch(u[s:s + step], i[s:s + step], ts[s:s + step], r[s:s + step])
+    A, B = a.to_csc(), b.to_csc()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+    assert (a.max_user_id, a.max_item_id, a.max_timestamp) == (b.max_user_id, b.max_item_id, b.max_timestamp)
+    assert a.all_item_ids == b.all_item_ids
+    assert list(a.hot_items.data.items()) == list(b.hot_items.data.items())
+    bad = u.copy(); bad[5] = 2**31
+    with pytest.raises(ValueError):
+        inter.UserItemInteractions().add_interactions_batch(bad, i, ts, r)
+
+
+def test_recommend_lists_chunked_pipeline_equals_single_launch(golden):
+    """SLIMElastic.recommend_lists (chunked launches + pinned D2H + host list building) returns what one
+    recommend_batch_device call returns, including lists shorter than k."""
+    from rtrec_b200.models import SLIM
+    z = golden("slim_nn20_cont")
+    ev = z["events"]
+    m = SLIM(nn_feature_selection=20)
+    m.add_interaction_arrays(ev[:, 0].astype(np.int64), ev[:, 1].astype(np.int64), ev[:, 2], ev[:, 3])
+    m.bulk_fit()
+    X = m.interactions.device_matrix()
+    users = np.arange(X.n_users, dtype=np.int64)
+    for dense in (False, True):
+        ids, _, cnt = m.model.recommend_batch_device(users, X, None, 10, True, dense)
+        want = [row[:c] for row, c in zip(ids.tolist(), cnt.tolist())]
+        old = m.model._LIST_CHUNK
+        try:
+            m.model._LIST_CHUNK = 37
+            got = m.model.recommend_lists(users, X, 10, True, dense)
+        finally:
+            m.model._LIST_CHUNK = old
+        assert got == want
+    ids, _, cnt = m.model.recommend_batch_device(np.arange(50), X, None, 10, True, False)
+    assert m.recommend_batch(list(range(50)), top_k=10) == [row[:c] for row, c in zip(ids.tolist(), cnt.tolist())]
