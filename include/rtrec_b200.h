@@ -263,6 +263,34 @@ int rt_slim_recommend(const int32_t *d_rptr, const int32_t *d_ridx, const float 
                       int32_t j_end, int32_t k, int32_t filter_interacted, int32_t mode,
                       int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt, void *stream);
 
+/*
+ * Scoring pack (score3.cu): the heavy rows of W (source items with >= min_row entries inside
+ * [j_begin, j_end)) re-packed per score tile as bank-striped ELL groups so that the shared-memory
+ * score update is conflict free and each entry is one 8-byte load.  Built once per W and item range:
+ *   rt_w_pack_plan  fills d_heavy_of[n_items] (heavy index or -1), d_heavy_list[n_items] (first
+ *                   *h_n_heavy entries valid) and d_ell_off[n_heavy * n_tiles + 1] (capacity
+ *                   n_items * n_tiles + 1 with n_tiles from rt_score_tile is always enough), returns the tile geometry and the number of
+ *                   32-slot groups; synchronises.
+ *   rt_w_pack_fill  writes the groups: d_ell holds *h_n_groups * 32 (column - tile start, float bits)
+ *                   int32 pairs, padding slots are (-1, 0); 8-byte aligned.
+ * rt_slim_recommend_packed is rt_slim_recommend with the pack; results are identical bit for bit.
+ */
+int rt_score_tile(int32_t n_items, int32_t j_begin, int32_t j_end, int32_t *h_tile, int32_t *h_n_tiles);
+int rt_w_pack_plan(const int32_t *d_wrptr, const int32_t *d_wridx, int32_t n_items, int32_t j_begin,
+                   int32_t j_end, int32_t min_row, int32_t *d_heavy_of, int32_t *d_heavy_list,
+                   int32_t *d_ell_off, int32_t *h_n_heavy, int32_t *h_tile, int32_t *h_n_tiles,
+                   int64_t *h_n_groups, void *stream);
+int rt_w_pack_fill(const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval, int32_t n_items,
+                   int32_t j_begin, int32_t j_end, const int32_t *d_heavy_list, int32_t n_heavy,
+                   const int32_t *d_ell_off, int32_t *d_ell, int64_t ell_cap_groups, void *stream);
+int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                             const int32_t *d_users, int32_t n_query, const int32_t *d_wrptr,
+                             const int32_t *d_wridx, const float *d_wrval, const int32_t *d_heavy_of,
+                             const int32_t *d_ell_off, const int32_t *d_ell, int32_t n_items,
+                             int32_t j_begin, int32_t j_end, int32_t k, int32_t filter_interacted,
+                             int32_t mode, int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt,
+                             void *stream);
+
 /* Candidate-restricted variant (slim_elastic.py:661-672, 722-739): dense scores of the
  * n_cand candidate items only, NO interacted filter, order (score desc, candidate position desc).
  * d_out_pos receives positions into the candidate list. */
@@ -283,8 +311,8 @@ int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d
                     const int32_t *d_items, int32_t n_query, int32_t k, int32_t *d_out_ids,
                     float *d_out_scores, int32_t *d_out_cnt, void *stream);
 
-/* Tuning switches: "score_impl" (1 = first-generation scoring kernel, 2 = staged/pipelined kernel,
- * default 2).  Returns RT_ERR_ARG for an unknown name. */
+/* Tuning switches: "score_impl" for rt_slim_recommend (1 = first-generation scoring kernel,
+ * 2 = staged/pipelined kernel, default 2; the packed third generation has its own entry point).  Returns RT_ERR_ARG for an unknown name. */
 int rt_set_option(const char *name, int32_t value);
 
 /* Frees the library-owned device scratch (grow-only arenas reused across calls). */

@@ -70,6 +70,12 @@ PROTOTYPES = {
     "rt_w_merge": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, C.POINTER(_I64), _P]),
     "rt_transpose": (C.c_int, [_I32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "rt_slim_recommend": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "rt_score_tile": (C.c_int, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
+    "rt_w_pack_plan": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32),
+                                 C.POINTER(_I64), _P]),
+    "rt_w_pack_fill": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _I32, _P, _P, _I64, _P]),
+    "rt_slim_recommend_packed": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32,
+                                           _P, _P, _P, _P]),
     "rt_slim_recommend_candidates": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P]),
     "rt_topk_merge": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "rt_slim_similar": (C.c_int, [_P, _P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _P]),

@@ -1,0 +1,432 @@
+// score3.cu -- K6 (v3): scoring with a bank-striped ELL pack for the heavy rows of W.
+//
+// Replaces /root/reference/rtrec/models/internal/slim_elastic.py:674-741 (recommend_batch:
+// safe_sparse_dot + per-user python top-k), :743-779 and :781-818, like score.cu / score2.cu, with
+// the same results bit for bit (same fp32 summation order per score: ascending source item).
+//
+// Why a third generation (profiles/r1g_*, r1j_*): at the ML-20M shape 99 % of the multiply-adds of
+// X.W come from the ~50 most popular source items, whose W rows hold thousands of entries (they are
+// a nearest neighbour of a quarter of all targets).  v2 streams those rows as (column, value) CSR
+// pairs and scatters into the shared-memory score tile: two global loads per entry and a
+// read-modify-write whose 32 lanes hit random banks (~3.5-way conflicts measured: 1.0e9 conflicts per
+// launch).  v3 re-packs every heavy row once per W, per score tile, as ELL groups of 32 slots where
+// slot `lane` only ever holds a column with (column - tile start) mod 32 == lane:
+//     * the tile update of a group is bank-conflict free by construction,
+//     * one 8-byte load per entry ((column, value) interleaved) instead of two 4-byte loads,
+//     * groups of a row are independent, so every warp keeps four loads in flight.
+// Rows are still applied one after the other in ascending item order (one barrier per row), light
+// rows exactly as in v2, so each score is the same fp32 sum scipy's csr_matmat produces.
+//
+// Algorithmic bytes per user: e*nnz(row u) + e*sum_{i in row u} nnz(W[i,:]) + 8k.
+#include <cub/cub.cuh>
+
+#include "block_select.cuh"
+#include "common.cuh"
+
+namespace rt {
+
+constexpr int S3_NT = 512;      // threads per CTA (2 CTAs/SM at the ML-20M tile size)
+constexpr int S3_NW = S3_NT / 32;
+constexpr int S3_CH = 512;      // interacted items staged per chunk
+constexpr int S3_GROUP = 8;     // light rows whose head entries are fetched together
+constexpr int KMAX3 = 128;
+
+struct Score3Shared {
+    union {
+        struct { int a[S3_CH]; int b[S3_CH]; float x[S3_CH]; } st;    // staging (b < 0: heavy row, a = first group, ~b = end group)
+        FastSelScratch fs;                                             // top-k
+        struct { uint32_t key[2 * KMAX3]; int idx[2 * KMAX3]; } tmp;   // tile merge
+    } u;
+    uint32_t best_key[2 * KMAX3];
+    int best_idx[2 * KMAX3];
+    int wsum[32];
+    int n_rows, q;
+};
+
+__device__ __forceinline__ float key_to_float3(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ int lower_bound3(const int *__restrict__ a, int lo, int hi, int v) {
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t elig_key3(float v, int mode) {
+    if (v == -INFINITY) return 0u;
+    if (mode == RT_TOPK_SPARSE && v == 0.0f) return 0u;
+    return float_key(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack construction
+// ------------------------------------------------------------------------------------------------
+
+// heavy flag per source item: entries inside [j_begin, j_end) >= min_row
+__global__ void pack_flag_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx, int n_items, int j_begin,
+                                 int j_end, int min_row, int *__restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    int a = wrptr[i], b = wrptr[i + 1];
+    if (b - a >= min_row && (j_begin > 0 || j_end < n_items)) {
+        a = lower_bound3(wridx, a, b, j_begin);
+        b = lower_bound3(wridx, a, b, j_end);
+    }
+    flag[i] = (b - a >= min_row) ? 1 : 0;
+}
+
+// heavy_of[i] = index among heavy rows or -1; heavy_list[h] = i
+__global__ void pack_index_kernel(const int *__restrict__ flag, const int *__restrict__ pos, int n_items,
+                                  int *__restrict__ heavy_of, int *__restrict__ heavy_list) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    if (flag[i]) { heavy_of[i] = pos[i]; heavy_list[pos[i]] = i; }
+    else heavy_of[i] = -1;
+}
+
+// one warp per (heavy row, tile): number of 32-slot groups = largest per-bank population
+__global__ void pack_count_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx,
+                                  const int *__restrict__ heavy_list, int n_heavy, int n_tiles, int j_begin, int j_end,
+                                  int tile, int *__restrict__ n_groups) {
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (w >= n_heavy * n_tiles) return;
+    const int h = w / n_tiles, tau = w - h * n_tiles;
+    const int i = heavy_list[h];
+    const int t0 = j_begin + tau * tile, t1 = min(t0 + tile, j_end);
+    int a = lower_bound3(wridx, wrptr[i], wrptr[i + 1], t0);
+    const int b = lower_bound3(wridx, a, wrptr[i + 1], t1);
+    int mine = 0;  // population of bank `lane`
+    for (int base = a; base < b; base += 32) {
+        const int e = base + lane;
+        const int bank = e < b ? ((wridx[e] - t0) & 31) : -1;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) mine += (__shfl_sync(0xffffffffu, bank, l) == lane);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    if (lane == 0) n_groups[w] = mine;
+}
+
+// one warp per (heavy row, tile): slot (position within bank, bank) <- (column - tile start, value); padding = (-1, 0)
+__global__ void pack_fill_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
+                                 const int *__restrict__ heavy_list, int n_heavy, int n_tiles, int j_begin, int j_end,
+                                 int tile, const int *__restrict__ ell_off, int2 *__restrict__ ell) {
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (w >= n_heavy * n_tiles) return;
+    const int h = w / n_tiles, tau = w - h * n_tiles;
+    const int i = heavy_list[h];
+    const int t0 = j_begin + tau * tile, t1 = min(t0 + tile, j_end);
+    int a = lower_bound3(wridx, wrptr[i], wrptr[i + 1], t0);
+    const int b = lower_bound3(wridx, a, wrptr[i + 1], t1);
+    const int g0 = ell_off[w], g1 = ell_off[w + 1];
+    int2 *out = ell + (size_t)g0 * 32;
+    for (int s = lane; s < (g1 - g0) * 32; s += 32) out[s] = make_int2(-1, 0);
+    __syncwarp();
+    int filled = 0;  // entries already placed in bank `lane`
+    for (int base = a; base < b; base += 32) {
+        const int e = base + lane;
+        int col = -1, bank = -1;
+        float v = 0.f;
+        if (e < b) { col = wridx[e] - t0; bank = col & 31; v = wrval[e]; }
+        // position inside the bank: entries of the same bank earlier in this batch + earlier batches
+        const unsigned same = __match_any_sync(0xffffffffu, bank);
+        const int before = __popc(same & ((1u << lane) - 1u));
+        const int prior = __shfl_sync(0xffffffffu, filled, bank < 0 ? 0 : bank);
+        if (e < b) out[(size_t)(prior + before) * 32 + bank] = make_int2(col, __float_as_int(v));
+        // update the per-bank counters: bank `lane` gains the number of lanes whose bank == lane
+        int gain = 0;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) gain += (__shfl_sync(0xffffffffu, bank, l) == lane);
+        filled += gain;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(S3_NT, 2)
+recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, const float *__restrict__ rval,
+                  const int *__restrict__ users, int n_query, const int *__restrict__ wrptr,
+                  const int *__restrict__ wridx, const float *__restrict__ wrval, const int *__restrict__ heavy_of,
+                  const int *__restrict__ ell_off, const int2 *__restrict__ ell, int n_tiles, int n_items, int j_begin,
+                  int j_end, int k, int filter, int mode, int tile, int *__restrict__ out_ids,
+                  float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ next_query) {
+    extern __shared__ __align__(16) float acc[];
+    __shared__ Score3Shared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh.q = atomicAdd(next_query, 1);
+        __syncthreads();
+        const int q = sh.q;
+        if (q >= n_query) break;
+        const int u = users[q];
+        const int r0 = rptr[u], r1 = rptr[u + 1];
+        int nbest = 0;
+        int tau = 0;
+        for (int t0 = j_begin; t0 < j_end; t0 += tile, ++tau) {
+            const int t1 = min(t0 + tile, j_end);
+            const int width = t1 - t0;
+            const bool whole = (t0 == 0 && t1 == n_items);
+            for (int x = tid; x < width; x += S3_NT) acc[x] = 0.0f;
+            // ---------------- accumulate: chunks of the user's row ----------------
+            for (int c0 = r0; c0 < r1; c0 += S3_CH) {
+                __syncthreads();  // previous chunk fully applied (and acc zeroed) before st.* is rewritten
+                {
+                    const int p = c0 + tid;
+                    int a = 0, b = 0;
+                    float x = 0.f;
+                    bool ne = false;
+                    if (p < r1 && tid < S3_CH) {
+                        const int i = ridx[p];
+                        x = rval[p];
+                        const int h = heavy_of[i];
+                        if (h >= 0) {
+                            a = ell_off[h * n_tiles + tau];
+                            const int ge = ell_off[h * n_tiles + tau + 1];
+                            ne = ge > a;
+                            b = ~ge;  // negative marks a heavy row
+                        } else {
+                            a = wrptr[i]; b = wrptr[i + 1];
+                            if (!whole && b > a) {
+                                a = lower_bound3(wridx, a, b, t0);
+                                b = lower_bound3(wridx, a, b, t1);
+                            }
+                            ne = b > a;
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, ne);
+                    if (lane == 0) sh.wsum[warp] = __popc(bal);
+                    __syncthreads();
+                    int off = 0, tot = 0;
+#pragma unroll
+                    for (int w = 0; w < S3_NW; ++w) { const int c = sh.wsum[w]; if (w < warp) off += c; tot += c; }
+                    if (ne) {
+                        const int s = off + __popc(bal & ((1u << lane) - 1u));
+                        sh.u.st.a[s] = a; sh.u.st.b[s] = b; sh.u.st.x[s] = x;
+                    }
+                    if (tid == 0) sh.n_rows = tot;
+                    __syncthreads();
+                }
+                const int n = sh.n_rows;
+                for (int g = 0; g < n; g += S3_GROUP) {
+                    int hj[S3_GROUP];
+                    float hv[S3_GROUP];
+                    // heads of up to 8 light rows: all loads are independent and issued back to back
+#pragma unroll
+                    for (int s = 0; s < S3_GROUP; ++s) {
+                        hj[s] = -1; hv[s] = 0.f;
+                        if (g + s < n) {
+                            const int b = sh.u.st.b[g + s];
+                            const int e = sh.u.st.a[g + s] + tid;
+                            if (b >= 0 && e < b) { hj[s] = wridx[e]; hv[s] = wrval[e]; }
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < S3_GROUP; ++s) {
+                        if (g + s < n) {   // uniform across the CTA
+                            const float x = sh.u.st.x[g + s];
+                            const int b = sh.u.st.b[g + s];
+                            if (b < 0) {
+                                // heavy row: warp w takes groups a+w, a+w+16, ...; four loads in flight
+                                const int ge = ~b;
+                                const int2 *base = ell + lane;
+                                int gi = sh.u.st.a[g + s] + warp;
+                                for (; gi + 3 * S3_NW < ge; gi += 4 * S3_NW) {
+                                    const int2 e0 = base[(size_t)gi * 32];
+                                    const int2 e1 = base[(size_t)(gi + S3_NW) * 32];
+                                    const int2 e2 = base[(size_t)(gi + 2 * S3_NW) * 32];
+                                    const int2 e3 = base[(size_t)(gi + 3 * S3_NW) * 32];
+                                    if (e0.x >= 0) acc[e0.x] = __fadd_rn(acc[e0.x], __fmul_rn(x, __int_as_float(e0.y)));
+                                    if (e1.x >= 0) acc[e1.x] = __fadd_rn(acc[e1.x], __fmul_rn(x, __int_as_float(e1.y)));
+                                    if (e2.x >= 0) acc[e2.x] = __fadd_rn(acc[e2.x], __fmul_rn(x, __int_as_float(e2.y)));
+                                    if (e3.x >= 0) acc[e3.x] = __fadd_rn(acc[e3.x], __fmul_rn(x, __int_as_float(e3.y)));
+                                }
+                                for (; gi < ge; gi += S3_NW) {
+                                    const int2 e0 = base[(size_t)gi * 32];
+                                    if (e0.x >= 0) acc[e0.x] = __fadd_rn(acc[e0.x], __fmul_rn(x, __int_as_float(e0.y)));
+                                }
+                            } else {
+                                if (hj[s] >= 0) { float *d = &acc[hj[s] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, hv[s])); }
+                                for (int e = sh.u.st.a[g + s] + tid + S3_NT; e < b; e += S3_NT) {
+                                    float *d = &acc[wridx[e] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, wrval[e]));
+                                }
+                            }
+                            __syncthreads();
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (filter) {
+                int fa = r0, fb = r1;
+                if (!whole) { fa = lower_bound3(ridx, r0, r1, t0); fb = lower_bound3(ridx, r0, r1, t1); }
+                for (int p = fa + tid; p < fb; p += S3_NT) acc[ridx[p] - t0] = -INFINITY;
+                __syncthreads();
+            }
+            // ---------------- top-k of the tile ----------------
+            auto key_of = [&](int idx) -> uint32_t { return elig_key3(acc[idx], mode); };
+            const int c = block_top_n_fast(width, k, key_of, &sh.u.fs, sh.best_idx + nbest, sh.best_key + nbest);
+            if (t0 != 0) {
+                for (int e = tid; e < c; e += S3_NT) sh.best_idx[nbest + e] += t0;
+                __syncthreads();
+            }
+            const int tot = nbest + c;
+            if (t0 != j_begin && c > 0) {
+                for (int e = tid; e < tot; e += S3_NT) {
+                    const uint32_t ke = sh.best_key[e];
+                    const int ie = sh.best_idx[e];
+                    int rank = 0;
+                    for (int f = 0; f < tot; ++f) rank += (sh.best_key[f] > ke) || (sh.best_key[f] == ke && sh.best_idx[f] > ie);
+                    if (rank < k) { sh.u.tmp.key[rank] = ke; sh.u.tmp.idx[rank] = ie; }
+                }
+                __syncthreads();
+                nbest = min(tot, k);
+                for (int e = tid; e < nbest; e += S3_NT) { sh.best_key[e] = sh.u.tmp.key[e]; sh.best_idx[e] = sh.u.tmp.idx[e]; }
+                __syncthreads();
+            } else nbest = tot;
+        }
+        for (int e = tid; e < k; e += S3_NT) {
+            out_ids[(size_t)q * k + e] = e < nbest ? sh.best_idx[e] : -1;
+            out_scores[(size_t)q * k + e] = e < nbest ? key_to_float3(sh.best_key[e]) : 0.0f;
+        }
+        if (tid == 0) out_cnt[q] = nbest;
+    }
+}
+
+// tile geometry shared by the pack builder and the launcher: two CTAs per SM share the shared memory
+static void score3_geometry(int width, int *tile, int *n_tiles) {
+    const int optin = rt::smem_optin();
+    const int static_bytes = (int)sizeof(Score3Shared) + 1024 + 64;
+    const int max_floats_2 = ((optin + 1024) / 2 - static_bytes) / 4;
+    int t = width, nt = 1;
+    if (width > max_floats_2) {
+        nt = (width + max_floats_2 - 1) / max_floats_2;
+        t = (width + nt - 1) / nt;
+    }
+    t = (t + 31) & ~31;  // bank alignment of every tile start
+    nt = width > 0 ? (width + t - 1) / t : 1;
+    *tile = t; *n_tiles = nt;
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+#define S3_CUB(call_expr)                                                                          \
+    do {                                                                                           \
+        size_t tmp_bytes__ = 0;                                                                    \
+        void *d_tmp__ = nullptr;                                                                   \
+        RT_CUDA(call_expr);                                                                        \
+        d_tmp__ = rt::scratch(SCR_CUB, tmp_bytes__);                                               \
+        if (!d_tmp__) return RT_ERR_CUDA;                                                          \
+        RT_CUDA(call_expr);                                                                        \
+        rt::count_launch(2);                                                                       \
+    } while (0)
+
+extern "C" int rt_score_tile(int32_t n_items, int32_t j_begin, int32_t j_end, int32_t *h_tile, int32_t *h_n_tiles) {
+    RT_ARG(n_items > 0 && j_begin >= 0 && j_end <= n_items && j_begin <= j_end && h_tile && h_n_tiles, "item range");
+    int tile = 0, n_tiles = 1;
+    score3_geometry(j_end - j_begin, &tile, &n_tiles);
+    *h_tile = tile; *h_n_tiles = n_tiles;
+    return RT_OK;
+}
+
+extern "C" int rt_w_pack_plan(const int32_t *d_wrptr, const int32_t *d_wridx, int32_t n_items, int32_t j_begin,
+                              int32_t j_end, int32_t min_row, int32_t *d_heavy_of, int32_t *d_heavy_list,
+                              int32_t *d_ell_off, int32_t *h_n_heavy, int32_t *h_tile, int32_t *h_n_tiles,
+                              int64_t *h_n_groups, void *stream) {
+    RT_ARG(n_items > 0 && j_begin >= 0 && j_end <= n_items && j_begin <= j_end, "item range");
+    RT_ARG(d_wrptr && d_heavy_of && d_heavy_list && d_ell_off, "null pointer");
+    RT_ARG(h_n_heavy && h_tile && h_n_tiles && h_n_groups, "host outputs");
+    if (min_row < 32) min_row = 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    int tile = 0, n_tiles = 1;
+    score3_geometry(j_end - j_begin, &tile, &n_tiles);
+    *h_tile = tile; *h_n_tiles = n_tiles; *h_n_heavy = 0; *h_n_groups = 0;
+    const int bs = 256;
+    int *flag = (int *)rt::scratch(SCR_WMAT_A, sizeof(int) * (2 * (size_t)n_items + 64));
+    if (!flag) return RT_ERR_CUDA;
+    int *pos = flag + n_items + 32;
+    pack_flag_kernel<<<(n_items + bs - 1) / bs, bs, 0, st>>>(d_wrptr, d_wridx, n_items, j_begin, j_end, min_row, flag);
+    RT_CHECK_LAUNCH();
+    S3_CUB(cub::DeviceScan::ExclusiveSum(d_tmp__, tmp_bytes__, flag, pos, n_items, st));
+    pack_index_kernel<<<(n_items + bs - 1) / bs, bs, 0, st>>>(flag, pos, n_items, d_heavy_of, d_heavy_list);
+    RT_CHECK_LAUNCH();
+    int last[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(&last[0], flag + n_items - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(&last[1], pos + n_items - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    const int n_heavy = last[0] + last[1];
+    *h_n_heavy = n_heavy;
+    RT_CUDA(cudaMemsetAsync(d_ell_off, 0, sizeof(int), st));
+    if (n_heavy == 0 || j_end == j_begin) return RT_OK;
+    const int n_w = n_heavy * n_tiles;
+    int *cnt = (int *)rt::scratch(SCR_WMAT_B, sizeof(int) * ((size_t)n_w + 64));
+    if (!cnt) return RT_ERR_CUDA;
+    pack_count_kernel<<<(unsigned)(((int64_t)n_w * 32 + bs - 1) / bs), bs, 0, st>>>(d_wrptr, d_wridx, d_heavy_list, n_heavy, n_tiles,
+                                                                                    j_begin, j_end, tile, cnt);
+    RT_CHECK_LAUNCH();
+    RT_CUDA(cudaMemsetAsync(cnt + n_w, 0, sizeof(int), st));
+    S3_CUB(cub::DeviceScan::ExclusiveSum(d_tmp__, tmp_bytes__, cnt, d_ell_off, n_w + 1, st));
+    int total = 0;
+    RT_CUDA(cudaMemcpyAsync(&total, d_ell_off + n_w, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    *h_n_groups = total;
+    return RT_OK;
+}
+
+extern "C" int rt_w_pack_fill(const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval, int32_t n_items,
+                              int32_t j_begin, int32_t j_end, const int32_t *d_heavy_list, int32_t n_heavy,
+                              const int32_t *d_ell_off, int32_t *d_ell, int64_t ell_cap_groups, void *stream) {
+    RT_ARG(n_items > 0 && j_begin >= 0 && j_end <= n_items && j_begin <= j_end, "item range");
+    if (n_heavy <= 0) return RT_OK;
+    RT_ARG(d_wrptr && d_wridx && d_wrval && d_heavy_list && d_ell_off && d_ell && ell_cap_groups > 0, "null pointer");
+    RT_ARG((((uintptr_t)d_ell) & 7) == 0, "d_ell must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int tile = 0, n_tiles = 1;
+    score3_geometry(j_end - j_begin, &tile, &n_tiles);
+    const int n_w = n_heavy * n_tiles, bs = 256;
+    pack_fill_kernel<<<(unsigned)(((int64_t)n_w * 32 + bs - 1) / bs), bs, 0, st>>>(d_wrptr, d_wridx, d_wrval, d_heavy_list, n_heavy,
+                                                                                   n_tiles, j_begin, j_end, tile, d_ell_off,
+                                                                                   (int2 *)d_ell);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                                        const int32_t *d_users, int32_t n_query, const int32_t *d_wrptr,
+                                        const int32_t *d_wridx, const float *d_wrval, const int32_t *d_heavy_of,
+                                        const int32_t *d_ell_off, const int32_t *d_ell, int32_t n_items,
+                                        int32_t j_begin, int32_t j_end, int32_t k, int32_t filter_interacted,
+                                        int32_t mode, int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt,
+                                        void *stream) {
+    RT_ARG(k >= 1 && k <= KMAX3, "k must be in [1,128]");
+    RT_ARG(n_items > 0 && j_begin >= 0 && j_end <= n_items && j_begin < j_end, "item range");
+    RT_ARG(mode == RT_TOPK_DENSE || mode == RT_TOPK_SPARSE, "mode");
+    if (n_query <= 0) return RT_OK;
+    RT_ARG(d_rptr && d_users && d_wrptr && d_heavy_of && d_ell_off && d_out_ids && d_out_scores && d_out_cnt, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_next = (int *)rt::scratch(SCR_MISC, 256);
+    if (!d_next) return RT_ERR_CUDA;
+    RT_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), st));
+    int tile = 0, n_tiles = 1;
+    score3_geometry(j_end - j_begin, &tile, &n_tiles);
+    const int optin = rt::smem_optin();
+    const int static_bytes = (int)sizeof(Score3Shared) + 1024 + 64;
+    const size_t smem = (size_t)tile * sizeof(float);
+    RT_CUDA(cudaFuncSetAttribute(recommend3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((size_t)(optin + 1024) / (smem + static_bytes));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int grid = rt::sm_count() * per_sm;
+    if (grid > n_query) grid = n_query;
+    recommend3_kernel<<<grid, S3_NT, smem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval,
+                                                d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles, n_items, j_begin, j_end,
+                                                k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}

@@ -134,7 +134,7 @@ extern "C" int rt_upload_events(const int64_t *h_users, const int64_t *h_items, 
     int T = n_threads;
     if (T <= 0) {
         const unsigned hc = std::thread::hardware_concurrency();
-        T = hc >= 16 ? 8 : (hc >= 4 ? (int)hc / 2 : 1);
+        T = hc >= 4 ? (int)(hc * 3 / 4) : 1;  // the pipeline is bound by host memory copies, not by PCIe
     }
     if (T > UP_MAX_THREADS) T = UP_MAX_THREADS;
     const int64_t n_chunks = (n + UP_CHUNK - 1) / UP_CHUNK;

@@ -126,6 +126,7 @@ class DeviceW:
     wrptr: object
     wridx: object
     wrval: object
+    packs: Optional[dict] = None   # (j_begin, j_end) -> ScorePack, built on first use
 
     def to_scipy_csc(self, dtype=np.float32):
         import scipy.sparse as sp
@@ -233,6 +234,12 @@ def gram_cols(X: DeviceMatrix, j_begin: int = 0, j_end: Optional[int] = None, ou
 
 
 def set_option(name: str, value: int) -> None:
+    """Tuning switches.  ``score_impl``: 3 = packed scoring kernel (default), 2 / 1 = earlier generations."""
+    global _score_impl
+    if name == "score_impl":
+        _score_impl = int(value)
+        if int(value) == 3:
+            return
     check(_lib.load().rt_set_option(name.encode(), int(value)), "rt_set_option")
 
 
@@ -297,6 +304,52 @@ def w_merge(old: Optional[DeviceW], n_items: int, res: SolveResult) -> DeviceW:
     return _finish_w(n_items, n, wptr, widx[:max(n, 1)], wval[:max(n, 1)])
 
 
+@dataclass
+class ScorePack:
+    """Bank-striped ELL pack of the heavy rows of W for one item range (score3.cu)."""
+    heavy_of: object   # int32 [n_items]
+    ell_off: object    # int32 [n_heavy * n_tiles + 1]
+    ell: object        # int32 [n_groups * 64] or None
+    n_heavy: int
+    n_groups: int
+    tile: int
+    n_tiles: int
+
+
+PACK_MIN_ROW = 768  # W rows shorter than this stay on the CSR path (one or two 512-thread steps)
+_score_impl = 3     # 3 = packed kernel (default), 2 / 1 = earlier generations through rt_slim_recommend
+
+
+def score_pack(W: DeviceW, j_begin: int, j_end: int) -> ScorePack:
+    if W.packs is None:
+        W.packs = {}
+    key = (int(j_begin), int(j_end))
+    hit = W.packs.get(key)
+    if hit is not None:
+        return hit
+    t = require_cuda()
+    lib = _lib.load()
+    I = W.n_items
+    heavy_of = empty(I, t.int32)
+    heavy_list = empty(I, t.int32)
+    n_heavy, tile, n_tiles, n_groups = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int64(0)
+    check(lib.rt_score_tile(I, key[0], key[1], C.byref(tile), C.byref(n_tiles)), "rt_score_tile")
+    ell_off = empty(I * max(int(n_tiles.value), 1) + 1, t.int32)
+    check(lib.rt_w_pack_plan(ptr(W.wrptr), ptr(W.wridx), I, key[0], key[1], PACK_MIN_ROW, ptr(heavy_of), ptr(heavy_list),
+                             ptr(ell_off), C.byref(n_heavy), C.byref(tile), C.byref(n_tiles), C.byref(n_groups),
+                             stream_ptr()), "rt_w_pack_plan")
+    ell = None
+    if n_heavy.value > 0 and n_groups.value > 0:
+        ell = empty(int(n_groups.value) * 64, t.int32)
+        check(lib.rt_w_pack_fill(ptr(W.wrptr), ptr(W.wridx), ptr(W.wrval), I, key[0], key[1], ptr(heavy_list),
+                                 int(n_heavy.value), ptr(ell_off), ptr(ell), int(n_groups.value), stream_ptr()),
+              "rt_w_pack_fill")
+    pack = ScorePack(heavy_of, ell_off[:int(n_heavy.value) * int(n_tiles.value) + 1], ell, int(n_heavy.value),
+                     int(n_groups.value), int(tile.value), int(n_tiles.value))
+    W.packs[key] = pack
+    return pack
+
+
 def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int,
               j_begin: int = 0, j_end: Optional[int] = None):
     """Fused scoring + filter + top-k for a batch of users (K6).  Returns device (ids, scores, cnt)."""
@@ -306,10 +359,18 @@ def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: boo
     scores = empty(max(Q * k, 1), t.float32)
     cnt = empty(max(Q, 1), t.int32)
     j_end = W.n_items if j_end is None else j_end
-    check(_lib.load().rt_slim_recommend(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr), ptr(W.wridx),
-                                        ptr(W.wrval), W.n_items, int(j_begin), int(j_end), int(k),
-                                        1 if filter_interacted else 0, int(mode), ptr(ids), ptr(scores), ptr(cnt),
-                                        stream_ptr()), "rt_slim_recommend")
+    if _score_impl == 3 and j_end > j_begin and Q > 0:
+        pk = score_pack(W, j_begin, j_end)
+        check(_lib.load().rt_slim_recommend_packed(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr),
+                                                   ptr(W.wridx), ptr(W.wrval), ptr(pk.heavy_of), ptr(pk.ell_off), ptr(pk.ell),
+                                                   W.n_items, int(j_begin), int(j_end), int(k),
+                                                   1 if filter_interacted else 0, int(mode), ptr(ids), ptr(scores),
+                                                   ptr(cnt), stream_ptr()), "rt_slim_recommend_packed")
+    else:
+        check(_lib.load().rt_slim_recommend(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr), ptr(W.wridx),
+                                            ptr(W.wrval), W.n_items, int(j_begin), int(j_end), int(k),
+                                            1 if filter_interacted else 0, int(mode), ptr(ids), ptr(scores), ptr(cnt),
+                                            stream_ptr()), "rt_slim_recommend")
     return ids.view(Q, k) if Q else ids[:0].view(0, k), scores.view(Q, k) if Q else scores[:0].view(0, k), cnt[:Q]
 
 

@@ -26,6 +26,9 @@ from ... import device as D
 from ..._lib import FitConfig, RT_TOPK_DENSE, RT_TOPK_SPARSE
 
 
+_PINNED: Dict[str, Any] = {}  # pinned host staging buffers for results (grow-only)
+
+
 def sklearn_seed(random_state) -> int:
     """What sklearn's Cython solver seeds its xorshift32 with for ``random_state``
     (``check_random_state(rs).randint(0, RAND_R_MAX)``, _cd_fast.pyx:748)."""
@@ -235,10 +238,10 @@ class SLIMElastic:
         k = max(1, min(int(top_k), 128))
         mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
         users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
-        pin = getattr(self, "_pin", None)
+        pin = _PINNED.get("lists")
         if pin is None or pin[0].numel() < Q * k or pin[1].numel() < Q:
             pin = (t.empty(Q * k, dtype=t.int32, pin_memory=True), t.empty(Q, dtype=t.int32, pin_memory=True))
-            self._pin = pin
+            _PINNED["lists"] = pin  # grow-only, shared by every model of the process (single caller thread)
         h_ids, h_cnt = pin[0][:Q * k].view(Q, k), pin[1][:Q]
         pending = []
         for a in range(0, Q, self._LIST_CHUNK):
@@ -255,8 +258,8 @@ class SLIMElastic:
             ev.synchronize()
             rows = ids_np[a:b].tolist()
             c = cnt_np[a:b]
-            if int(c.min()) < k:
-                rows = [row if n == k else row[:n] for row, n in zip(rows, c.tolist())]
+            for r in np.flatnonzero(c < k).tolist():  # lists shorter than k: drop the -1 padding
+                del rows[r][int(c[r]):]
             out.extend(rows)
         return out
 
@@ -264,7 +267,6 @@ class SLIMElastic:
         st = dict(self.__dict__)
         st["_W_host"] = self.item_similarity
         st["_W"] = None
-        st.pop("_pin", None)
         return st
 
     def similar_items(self, item_id: int, top_k: int = 10, ret_ndarrays: bool = False):

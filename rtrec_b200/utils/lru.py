@@ -77,13 +77,20 @@ class LRUFreqSet(MutableSet):
         """Apply a batch summarised as (distinct key, number of adds, arrival index of its last add).
         Same end state as the event-by-event loop provided no eviction can occur; returns False
         (and changes nothing) when one could, so the caller replays the events one by one."""
+        data = self.data
+        if not data:
+            # empty set (first batch of a bulk fit): the result is simply the keys in last-touch order
+            if len(uniq) > self.capacity:
+                return False
+            order = np.argsort(last, kind="stable")
+            data.update(zip(np.asarray(uniq)[order].tolist(), np.asarray(counts)[order].tolist()))
+            return True
         keys = uniq.tolist()
-        n_fresh = sum(1 for k in keys if k not in self.data)
-        if len(self.data) + n_fresh > self.capacity:
+        n_fresh = len(keys) - sum(map(data.__contains__, keys))
+        if len(data) + n_fresh > self.capacity:
             return False
         # no eviction: counters add up, touched keys move to the MRU end ordered by last touch
         cnt = counts.tolist()
-        data = self.data
         for j in np.argsort(last, kind="stable").tolist():
             key = keys[j]
             data[key] = data.pop(key, 0) + cnt[j]

@@ -284,3 +284,62 @@ def test_shard_merge_equals_single_pass(golden):
         assert t.equal(m_cnt, full_cnt)
         assert t.equal(m_ids, full_ids)
         assert t.equal(m_sc, full_sc)
+
+
+# ------------------------------------------------------------------------------------------ packed scoring (score3.cu)
+@pytest.mark.parametrize("n_items,j_range", [(3000, None), (3000, (512, 2500)), (61000, None), (61000, (1000, 60001))])
+def test_packed_scoring_equals_csr_scoring(n_items, j_range):
+    """The bank-striped ELL pack changes the layout of W's heavy rows, not the arithmetic: ids, scores and
+    counts equal the v2 kernel bit for bit (single tile, item sub-range, several tiles), and the scores equal
+    a float32 numpy accumulation in ascending item order."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200._lib import RT_TOPK_DENSE, RT_TOPK_SPARSE
+    rng = np.random.default_rng(n_items)
+    n_users = 700
+    # W: 12 heavy source rows (a quarter of the columns each) + a sparse background
+    rows, cols, vals = [], [], []
+    heavy = rng.choice(n_items, 12, replace=False)
+    for i in heavy:
+        c = np.flatnonzero(rng.random(n_items) < 0.25)
+        rows.append(np.full(len(c), i)); cols.append(c); vals.append(rng.random(len(c)).astype(np.float32))
+    nb = 5 * n_items
+    rows.append(rng.integers(0, n_items, nb)); cols.append(rng.integers(0, n_items, nb)); vals.append(rng.random(nb).astype(np.float32))
+    W = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_items, n_items))
+    W.sum_duplicates()
+    # X: every user rates ~40 random items plus a few of the heavy ones
+    xr = np.repeat(np.arange(n_users), 44)
+    xc = np.concatenate([np.concatenate([rng.choice(n_items, 40, replace=False), rng.choice(heavy, 4, replace=False)])
+                         for _ in range(n_users)])
+    X = sp.csr_matrix((rng.integers(1, 6, len(xr)).astype(np.float32), (xr, xc)), shape=(n_users, n_items))
+    X.sum_duplicates()
+    dX, dW = D.DeviceMatrix.from_scipy(X), D.DeviceW.from_scipy(W)
+    users = torch.arange(n_users, dtype=torch.int32, device="cuda")
+    j0, j1 = (0, n_items) if j_range is None else j_range
+    old_min = D.PACK_MIN_ROW
+    try:
+        D.PACK_MIN_ROW = 64
+        for mode in (RT_TOPK_SPARSE, RT_TOPK_DENSE):
+            for filt in (True, False):
+                D.set_option("score_impl", 2)
+                a = [x.cpu().numpy() for x in D.recommend(dX, users, dW, 10, filt, mode, j0, j1)]
+                D.set_option("score_impl", 3)
+                b = [x.cpu().numpy() for x in D.recommend(dX, users, dW, 10, filt, mode, j0, j1)]
+                for x, y in zip(a, b):
+                    assert np.array_equal(x, y)
+        pk = D.score_pack(dW, j0, j1)
+        assert pk.n_heavy >= 12 and pk.n_groups > 0
+    finally:
+        D.PACK_MIN_ROW = old_min
+        D.set_option("score_impl", 3)
+    # exact scores of a few users: ascending-item float32 accumulation (scipy csr_matmat order)
+    Wr = W.tocsr(); Wr.sort_indices()
+    ids, scores, cnt = b
+    for u in range(0, n_users, 97):
+        s = np.zeros(n_items, dtype=np.float32)
+        for p in range(X.indptr[u], X.indptr[u + 1]):
+            i, x = X.indices[p], X.data[p]
+            sl = slice(Wr.indptr[i], Wr.indptr[i + 1])
+            s[Wr.indices[sl]] = s[Wr.indices[sl]] + np.float32(x) * Wr.data[sl]
+        for e in range(cnt[u]):
+            assert scores[u, e] == s[ids[u, e]]

@@ -90,6 +90,15 @@ def main():
             D.set_option("score_impl", 2)
             ms2, o2 = timeit(lambda: D.recommend(X, users, W, 10, True, mode))
             res[f"score_{name}_v1_ms"] = ms1; res[f"score_{name}_v2_ms"] = ms2
+            D.set_option("score_impl", 3)
+            for min_row in (512, 768, 1536, 3072):
+                D.PACK_MIN_ROW = min_row
+                W.packs = None
+                ms3, o3 = timeit(lambda: D.recommend(X, users, W, 10, True, mode))
+                pk = D.score_pack(W, 0, I)
+                res[f"score_{name}_v3_min{min_row}"] = {"ms": ms3, "n_heavy": pk.n_heavy, "n_groups": pk.n_groups,
+                                                         "equal": bool(torch.equal(o3[0], o2[0]) and torch.equal(o3[1], o2[1]) and torch.equal(o3[2], o2[2]))}
+            D.PACK_MIN_ROW = 768
             res[f"score_{name}_equal"] = bool(torch.equal(o1[0], o2[0]) and torch.equal(o1[1], o2[1]) and torch.equal(o1[2], o2[2]))
             if not res[f"score_{name}_equal"]:
                 bad = (o1[0] != o2[0]).any(dim=1).nonzero().flatten()
