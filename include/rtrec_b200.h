@@ -271,8 +271,9 @@ int rt_slim_recommend(const int32_t *d_rptr, const int32_t *d_ridx, const float 
  *                   *h_n_heavy entries valid) and d_ell_off[n_heavy * n_tiles + 1] (capacity
  *                   n_items * n_tiles + 1 with n_tiles from rt_score_tile is always enough), returns the tile geometry and the number of
  *                   32-slot groups; synchronises.
- *   rt_w_pack_fill  writes the groups: d_ell holds *h_n_groups * 32 (column - tile start, float bits)
- *                   int32 pairs, padding slots are (-1, 0); 8-byte aligned.
+ *   rt_w_pack_fill  writes the groups: d_ell holds *h_n_groups * 32 (byte offset of the column inside its
+ *                   score tile, float bits) int32 pairs; padding slots carry value 0 and point at a
+ *                   dummy float behind the tile; 8-byte aligned.
  * rt_slim_recommend_packed is rt_slim_recommend with the pack; results are identical bit for bit.
  */
 int rt_score_tile(int32_t n_items, int32_t j_begin, int32_t j_end, int32_t *h_tile, int32_t *h_n_tiles);

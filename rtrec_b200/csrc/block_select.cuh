@@ -319,4 +319,113 @@ __device__ int block_top_n_fast(int N, int n, KeyFn key_of, FastSelScratch *fs, 
     return kk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Same selection over a float array in shared memory (the score tile), with the two scans done on raw
+// floats: an element is eligible iff v > -inf and, when skip_zero, v != 0.  Order-preserving keys are
+// formed only for bucket maxima and collected elements, which takes the key transform out of the
+// per-element loops (it was a third of the scoring kernel's instructions, profiles/r1l_*).  Results are
+// identical to block_top_n_fast with key_of(x) = eligible ? float_key(v[x]) : 0; every unusual case
+// (n > 128, list overflow through ties) is handed to that function.
+__device__ __forceinline__ float fs_key_to_float(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool skip_zero, FastSelScratch *fs, int *out_idx,
+                                    uint32_t *out_key) {
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = (NT + 31) >> 5;
+    if (n <= 0 || N <= 0) return 0;
+    auto key_of = [&](int x) -> uint32_t {
+        const float v = vals[x];
+        if (!(v > -INFINITY) || (skip_zero && v == 0.0f)) return 0u;
+        return float_key(v);
+    };
+    if (n > FS_BUCKETS || (NT % FS_BUCKETS) != 0 || N < 4 * FS_BUCKETS)
+        return block_top_n_fast(N, n, key_of, fs, out_idx, out_key);
+    __syncthreads();
+    if (tid < FS_BUCKETS) fs->u.f.bmax[tid] = 0u;
+    if (tid == 0) { fs->cnt_gt = 0; fs->cnt_ge = 0; }
+    __syncthreads();
+    // ---- pass 1: bucket maxima (on floats) and eligible count ----------------------------------------
+    float m = -INFINITY;
+    int ne = 0;
+    if (skip_zero) {
+#pragma unroll 8
+        for (int x = tid; x < N; x += NT) {
+            const float v = vals[x];
+            const bool ok = (v > -INFINITY) && (v != 0.0f);
+            m = ok ? fmaxf(m, v) : m;
+            ne += ok;
+        }
+    } else {
+#pragma unroll 8
+        for (int x = tid; x < N; x += NT) {
+            const float v = vals[x];
+            const bool ok = v > -INFINITY;
+            m = ok ? fmaxf(m, v) : m;
+            ne += ok;
+        }
+    }
+    if (ne) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], float_key(m));
+    ne = warp_sum_i(ne);
+    if (lane == 0) fs->wtot[0][warp] = ne;
+    __syncthreads();
+    int n_elig = 0;
+    for (int w = 0; w < nwarps; ++w) n_elig += fs->wtot[0][w];
+    const int kk = min(n, n_elig);
+    if (kk == 0) return 0;
+    if (tid < FS_BUCKETS) {
+        const uint32_t bm = fs->u.f.bmax[tid];
+        int rank = 0;
+        for (int f = 0; f < FS_BUCKETS; ++f) {
+            const uint32_t kf = fs->u.f.bmax[f];
+            rank += (kf > bm) || (kf == bm && f < tid);
+        }
+        if (rank == kk - 1) fs->T = bm == 0u ? 1u : bm;
+    }
+    __syncthreads();
+    const uint32_t T = fs->T;
+    // T is the key of an eligible element here (kk <= number of non-empty buckets is not guaranteed: with fewer
+    // non-empty buckets than kk the kk-th maximum is 0 -> T = 1, below every eligible key)
+    const float Tf = T > 1u ? fs_key_to_float(T) : -INFINITY;
+    // ---- pass 2: collect everything >= T ---------------------------------------------------------------
+    for (int base = 0; base < N; base += NT) {
+        const int x = base + tid;
+        float v = -INFINITY;
+        if (x < N) v = vals[x];
+        bool take = (v >= Tf) && (v > -INFINITY);
+        if (skip_zero) take = take && (v != 0.0f);
+        const unsigned bal = __ballot_sync(0xffffffffu, take);
+        if (bal) {
+            const uint32_t key = take ? float_key(v) : 0u;
+            const unsigned bgt = __ballot_sync(0xffffffffu, key > T);
+            int basepos = 0;
+            if (lane == 0) {
+                basepos = atomicAdd(&fs->cnt_ge, __popc(bal));
+                if (bgt) atomicAdd(&fs->cnt_gt, __popc(bgt));
+            }
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            const int pos = take ? basepos + __popc(bal & ((1u << lane) - 1u)) : FS_LIST;
+            if (pos < FS_LIST) { fs->u.f.lkey[pos] = key; fs->u.f.lidx[pos] = x; }
+        }
+    }
+    __syncthreads();
+    const int total = fs->cnt_ge;
+    if (total > FS_LIST) return block_top_n_fast(N, n, key_of, fs, out_idx, out_key);  // massive ties: generic path
+    // ---- rank sort -------------------------------------------------------------------------------------
+    for (int e = tid; e < total; e += NT) {
+        const uint32_t ke = fs->u.f.lkey[e];
+        const int ie = fs->u.f.lidx[e];
+        int rank = 0;
+        for (int f = 0; f < total; ++f) {
+            const uint32_t kf = fs->u.f.lkey[f];
+            const int jf = fs->u.f.lidx[f];
+            rank += (kf > ke) || (kf == ke && jf > ie);
+        }
+        if (rank < kk) { out_idx[rank] = ie; if (out_key) out_key[rank] = ke; }
+    }
+    __syncthreads();
+    return kk;
+}
+
 }  // namespace rt

@@ -53,12 +53,6 @@ __device__ __forceinline__ int lower_bound3(const int *__restrict__ a, int lo, i
     return lo;
 }
 
-__device__ __forceinline__ uint32_t elig_key3(float v, int mode) {
-    if (v == -INFINITY) return 0u;
-    if (mode == RT_TOPK_SPARSE && v == 0.0f) return 0u;
-    return float_key(v);
-}
-
 // ------------------------------------------------------------------------------------------------
 // pack construction
 // ------------------------------------------------------------------------------------------------
@@ -109,7 +103,9 @@ __global__ void pack_count_kernel(const int *__restrict__ wrptr, const int *__re
     if (lane == 0) n_groups[w] = mine;
 }
 
-// one warp per (heavy row, tile): slot (position within bank, bank) <- (column - tile start, value); padding = (-1, 0)
+// one warp per (heavy row, tile): slot (position within bank, bank) <- (byte offset of the column in the score
+// tile, value); a padding slot points at the lane's own dummy float behind the tile with value 0, so the
+// scoring loop needs no predicate
 __global__ void pack_fill_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
                                  const int *__restrict__ heavy_list, int n_heavy, int n_tiles, int j_begin, int j_end,
                                  int tile, const int *__restrict__ ell_off, int2 *__restrict__ ell) {
@@ -123,7 +119,7 @@ __global__ void pack_fill_kernel(const int *__restrict__ wrptr, const int *__res
     const int b = lower_bound3(wridx, a, wrptr[i + 1], t1);
     const int g0 = ell_off[w], g1 = ell_off[w + 1];
     int2 *out = ell + (size_t)g0 * 32;
-    for (int s = lane; s < (g1 - g0) * 32; s += 32) out[s] = make_int2(-1, 0);
+    for (int s = lane; s < (g1 - g0) * 32; s += 32) out[s] = make_int2((tile + lane) * 4, 0);
     __syncwarp();
     int filled = 0;  // entries already placed in bank `lane`
     for (int base = a; base < b; base += 32) {
@@ -135,7 +131,7 @@ __global__ void pack_fill_kernel(const int *__restrict__ wrptr, const int *__res
         const unsigned same = __match_any_sync(0xffffffffu, bank);
         const int before = __popc(same & ((1u << lane) - 1u));
         const int prior = __shfl_sync(0xffffffffu, filled, bank < 0 ? 0 : bank);
-        if (e < b) out[(size_t)(prior + before) * 32 + bank] = make_int2(col, __float_as_int(v));
+        if (e < b) out[(size_t)(prior + before) * 32 + bank] = make_int2(col * 4, __float_as_int(v));
         // update the per-bank counters: bank `lane` gains the number of lanes whose bank == lane
         int gain = 0;
 #pragma unroll
@@ -234,21 +230,34 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                                 // heavy row: warp w takes groups a+w, a+w+16, ...; four loads in flight
                                 const int ge = ~b;
                                 const int2 *base = ell + lane;
+                                char *accb = (char *)acc;
                                 int gi = sh.u.st.a[g + s] + warp;
-                                for (; gi + 3 * S3_NW < ge; gi += 4 * S3_NW) {
-                                    const int2 e0 = base[(size_t)gi * 32];
-                                    const int2 e1 = base[(size_t)(gi + S3_NW) * 32];
-                                    const int2 e2 = base[(size_t)(gi + 2 * S3_NW) * 32];
-                                    const int2 e3 = base[(size_t)(gi + 3 * S3_NW) * 32];
-                                    if (e0.x >= 0) acc[e0.x] = __fadd_rn(acc[e0.x], __fmul_rn(x, __int_as_float(e0.y)));
-                                    if (e1.x >= 0) acc[e1.x] = __fadd_rn(acc[e1.x], __fmul_rn(x, __int_as_float(e1.y)));
-                                    if (e2.x >= 0) acc[e2.x] = __fadd_rn(acc[e2.x], __fmul_rn(x, __int_as_float(e2.y)));
-                                    if (e3.x >= 0) acc[e3.x] = __fadd_rn(acc[e3.x], __fmul_rn(x, __int_as_float(e3.y)));
+#define S3_APPLY(E) { float *d = (float *)(accb + (E).x); *d = __fadd_rn(*d, __fmul_rn(x, __int_as_float((E).y))); }
+                                for (; gi + 7 * S3_NW < ge; gi += 8 * S3_NW) {
+                                    int2 e[8];
+#pragma unroll
+                                    for (int r = 0; r < 8; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32];
+#pragma unroll
+                                    for (int r = 0; r < 8; ++r) S3_APPLY(e[r]);
                                 }
-                                for (; gi < ge; gi += S3_NW) {
-                                    const int2 e0 = base[(size_t)gi * 32];
-                                    if (e0.x >= 0) acc[e0.x] = __fadd_rn(acc[e0.x], __fmul_rn(x, __int_as_float(e0.y)));
+                                if (gi + 3 * S3_NW < ge) {
+                                    int2 e[4];
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32];
+#pragma unroll
+                                    for (int r = 0; r < 4; ++r) S3_APPLY(e[r]);
+                                    gi += 4 * S3_NW;
                                 }
+                                {
+                                    // up to three groups left: loads first, then the updates
+                                    int2 e[3];
+#pragma unroll
+                                    for (int r = 0; r < 3; ++r)
+                                        e[r] = (gi + r * S3_NW < ge) ? base[(size_t)(gi + r * S3_NW) * 32] : make_int2((tile + lane) * 4, 0);
+#pragma unroll
+                                    for (int r = 0; r < 3; ++r) S3_APPLY(e[r]);
+                                }
+#undef S3_APPLY
                             } else {
                                 if (hj[s] >= 0) { float *d = &acc[hj[s] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, hv[s])); }
                                 for (int e = sh.u.st.a[g + s] + tid + S3_NT; e < b; e += S3_NT) {
@@ -268,8 +277,8 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                 __syncthreads();
             }
             // ---------------- top-k of the tile ----------------
-            auto key_of = [&](int idx) -> uint32_t { return elig_key3(acc[idx], mode); };
-            const int c = block_top_n_fast(width, k, key_of, &sh.u.fs, sh.best_idx + nbest, sh.best_key + nbest);
+            const int c = block_top_n_fast_f32(acc, width, k, mode == RT_TOPK_SPARSE, &sh.u.fs, sh.best_idx + nbest,
+                                               sh.best_key + nbest);
             if (t0 != 0) {
                 for (int e = tid; e < c; e += S3_NT) sh.best_idx[nbest + e] += t0;
                 __syncthreads();
@@ -301,7 +310,7 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
 static void score3_geometry(int width, int *tile, int *n_tiles) {
     const int optin = rt::smem_optin();
     const int static_bytes = (int)sizeof(Score3Shared) + 1024 + 64;
-    const int max_floats_2 = ((optin + 1024) / 2 - static_bytes) / 4;
+    const int max_floats_2 = ((optin + 1024) / 2 - static_bytes) / 4 - 32;  // 32 dummy floats behind the tile
     int t = width, nt = 1;
     if (width > max_floats_2) {
         nt = (width + max_floats_2 - 1) / max_floats_2;
@@ -417,7 +426,7 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
     score3_geometry(j_end - j_begin, &tile, &n_tiles);
     const int optin = rt::smem_optin();
     const int static_bytes = (int)sizeof(Score3Shared) + 1024 + 64;
-    const size_t smem = (size_t)tile * sizeof(float);
+    const size_t smem = (size_t)(tile + 32) * sizeof(float);
     RT_CUDA(cudaFuncSetAttribute(recommend3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((size_t)(optin + 1024) / (smem + static_bytes));
     if (per_sm < 1) per_sm = 1;

@@ -10,6 +10,11 @@ METRICS = [
     ("dram__bytes_write.sum", "DRAM write"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % of peak"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("lts__t_bytes.sum", "L2 bytes"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->L1 read bytes"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),

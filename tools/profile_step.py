@@ -9,6 +9,8 @@ from rtrec_b200._lib import RT_TOPK_SPARSE
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "ml20m"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+if len(sys.argv) > 3:
+    D.set_option("score_impl", int(sys.argv[3]))
 shape, kwargs, desc = bench.WORKLOADS[wl]
 u, i, ts, r = bench.load_events(shape)
 U = int(u.max()) + 1
