@@ -195,15 +195,11 @@ def run_ours(args):
         cfg = op._config(X)
         t = torch
         j0, j1 = P.item_shard(X.n_items, rank, world)
-        L = D.gram_lower(X, part=rank, n_parts=world)
-        mark("gram_lower")
-        if world > 1:
-            P.exchange_slabs(L.Gp, L.cuts)
-            mark("gram_exchange")
-        G = D.gram_finish(L)
-        del L
-        mark("gram_finish")
-        tg = t.arange(j0, j1, dtype=t.int32, device="cuda")
+        G = P.gram_sharded(X, rank=rank, world=world, exchange=args.exchange, marks=mark)
+        if world > 1 and args.scoring == "query":
+            tg = P.item_stride(X.n_items, rank, world)   # interleaved targets: balanced whatever the id order
+        else:
+            tg = t.arange(j0, j1, dtype=t.int32, device="cuda")
         res = D.solve(G, X.n_items, tg, cfg)
         mark("solve")
         del G
@@ -280,7 +276,7 @@ def run_ours(args):
     nn = kwargs.get("nn_feature_selection") or X.n_items
     m_live = stats[:, 3]
     solve_bytes = float((4.0 * X.n_items + 4.0 * (m_live * m_live + m_live) + e_bytes * nn).sum())
-    gram_ms = phase_ms.get("gram_lower", 0.0) + phase_ms.get("gram_finish", 0.0)
+    gram_ms = phase_ms.get("gram_lower", 0.0) + phase_ms.get("gram_finish", 0.0) + phase_ms.get("gram_finish_p2p", 0.0)
     kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0), solve_bytes), "recommend": (rec_ms, rec_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9
@@ -383,6 +379,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml20m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: Gram slab exchange fused with the mirror kernel over peer memory (default) or NCCL broadcasts")
     ap.add_argument("--scoring", default="query", choices=["query", "item"],
                     help="N>1: partition scoring by query users (W all-gathered, default) or by item columns (top-k merge)")
     args = ap.parse_args()

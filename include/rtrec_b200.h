@@ -172,6 +172,36 @@ int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_
                    const int32_t *d_orig_of, float *d_G, int64_t ldg, void *stream);
 
 /*
+ * Multi-GPU form of rt_gram_finish: the slab exchange is fused with the mirror step over peer memory.
+ * h_slabs[p] (HOST array of n_parts DEVICE pointers, p = part index) addresses the d_Gp buffer of rank p
+ * as seen from this process: the own buffer for p == part, a CUDA IPC mapping (rt_ipc_open) of the
+ * peer's buffer otherwise; all have the same ldgp.  Rows [h_cuts[p], h_cuts[p+1]) of the lower triangle
+ * are read from slab p (NVLink P2P loads for p != part), stored into the own buffer and mirrored into
+ * its upper triangle in one pass; with unpermute != 0 the symmetric matrix is then written in the
+ * caller's item ids to d_G exactly like rt_gram_finish.  The caller orders the ranks: every rank must
+ * have finished rt_gram_lower before any rank starts this call, and no rank may overwrite its slab
+ * until every rank has finished it (two stream-ordered barriers, e.g. a one-element NCCL all-reduce).
+ */
+#define RT_MAX_PEERS 8
+int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part,
+                       const int32_t *h_cuts, int64_t ldgp, const int32_t *d_rank_of,
+                       const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t unpermute, void *stream);
+
+/*
+ * Device buffers that other processes of the same node can map (CUDA IPC): rt_ipc_alloc returns a
+ * cudaMalloc'ed pointer and its 64-byte handle; a peer process passes the handle to rt_ipc_open and
+ * gets a pointer valid in its own address space (peer access over NVLink is enabled on demand).
+ * rt_ipc_close unmaps, rt_ipc_free releases the owner's allocation.  rt_memset is cudaMemsetAsync for
+ * such raw buffers.
+ */
+#define RT_IPC_HANDLE_BYTES 64
+int rt_ipc_alloc(size_t bytes, void **d_ptr, uint8_t *h_handle);
+int rt_ipc_open(const uint8_t *h_handle, void **d_ptr);
+int rt_ipc_close(void *d_ptr);
+int rt_ipc_free(void *d_ptr);
+int rt_memset(void *d_ptr, int32_t value, size_t bytes, void *stream);
+
+/*
  * Range-split row pointers of a CSR/CSC matrix with ascending minor indices:
  * d_seg[row * (n_ranges + 1) + g] = first position of `row` whose minor index is
  * >= base + g * range_width.  Helper of rt_gram; exported for tests.

@@ -104,3 +104,41 @@ extern "C" void rt_release_scratch(void) {
 }
 extern "C" int64_t rt_launch_count(void) { return (int64_t)rt::g_launches.load(); }
 extern "C" void rt_launch_count_reset(void) { rt::g_launches.store(0); }
+
+// ---- CUDA IPC buffers (multi-GPU slab exchange over peer memory, gram3.cu) ---------------------------
+extern "C" int rt_ipc_alloc(size_t bytes, void **d_ptr, uint8_t *h_handle) {
+    RT_ARG(bytes > 0 && d_ptr && h_handle, "arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RT_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = nullptr;
+    RT_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        rt::set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return RT_ERR_CUDA;
+    }
+    memcpy(h_handle, &h, sizeof(h));
+    *d_ptr = p;
+    return RT_OK;
+}
+extern "C" int rt_ipc_open(const uint8_t *h_handle, void **d_ptr) {
+    RT_ARG(h_handle && d_ptr, "arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof(h));
+    RT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+extern "C" int rt_ipc_close(void *d_ptr) {
+    if (d_ptr) RT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return RT_OK;
+}
+extern "C" int rt_ipc_free(void *d_ptr) {
+    if (d_ptr) RT_CUDA(cudaFree(d_ptr));
+    return RT_OK;
+}
+extern "C" int rt_memset(void *d_ptr, int32_t value, size_t bytes, void *stream) {
+    RT_ARG(d_ptr || bytes == 0, "null pointer");
+    if (bytes) RT_CUDA(cudaMemsetAsync(d_ptr, value, bytes, (cudaStream_t)stream));
+    return RT_OK;
+}

@@ -244,6 +244,42 @@ __global__ void __launch_bounds__(256) gram_mirror_kernel(float *__restrict__ G,
     }
 }
 
+// Multi-GPU: fused slab exchange + mirror over peer memory.  Rank `me` holds its own row slab of the lower
+// triangle; the slabs of the other ranks are read straight out of their memory (CUDA IPC mappings, NVLink
+// P2P loads) tile by tile while the tile is being mirrored, so every element of the triangle crosses
+// NVLink once per destination and there is no separate all-gather pass: the lower tile is stored locally
+// (if it came from a peer) together with its transpose in the upper triangle.
+struct GramPeers {
+    const float *src[RT_MAX_PEERS];
+    int cuts[RT_MAX_PEERS + 1];
+    int n_parts;
+    int me;
+};
+
+__global__ void __launch_bounds__(256) gram_pull_mirror_kernel(GramPeers P, float *__restrict__ G, int n, int64_t ld) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int row = by * 32 + r, col = bx * 32 + tx;
+        float v = 0.0f;
+        if (row < n && col <= row) {
+            int owner = 0;
+#pragma unroll
+            for (int p = 1; p < RT_MAX_PEERS; ++p) owner += (p < P.n_parts && row >= P.cuts[p]) ? 1 : 0;
+            v = P.src[owner][(size_t)row * ld + col];
+            if (owner != P.me) G[(size_t)row * ld + col] = v;
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int row = bx * 32 + r, col = by * 32 + tx;  // destination (upper)
+        if (row < n && col < n && col > row) G[(size_t)row * ld + col] = tile[tx][r];
+    }
+}
+
 // G[orig_of[jp]][x] = G'[jp][rank_of[x]]: one CTA per row; the row is staged in shared memory when it fits
 __global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n,
                                                               const int *__restrict__ rank_of, const int *__restrict__ orig_of,
@@ -383,6 +419,32 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
     return RT_OK;
 }
 
+static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                            const int32_t *d_orig_of, float *d_G, int64_t ldg, cudaStream_t st) {
+    return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
+}
+
+extern "C" int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part,
+                                  const int32_t *h_cuts, int64_t ldgp, const int32_t *d_rank_of,
+                                  const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t unpermute, void *stream) {
+    RT_ARG(n_items > 0 && h_slabs && h_cuts && ldgp >= n_items, "arguments");
+    RT_ARG(n_parts >= 1 && n_parts <= RT_MAX_PEERS && part >= 0 && part < n_parts, "part / n_parts");
+    for (int p = 0; p < n_parts; ++p) RT_ARG(h_slabs[p] != nullptr && h_cuts[p] <= h_cuts[p + 1], "slab pointers / cuts");
+    RT_ARG(h_cuts[0] == 0 && h_cuts[n_parts] == n_items, "cuts must cover [0, n_items]");
+    cudaStream_t st = (cudaStream_t)stream;
+    GramPeers P;
+    for (int p = 0; p < RT_MAX_PEERS; ++p) { P.src[p] = (const float *)h_slabs[p < n_parts ? p : 0]; P.cuts[p] = p <= n_parts ? h_cuts[p] : n_items; }
+    P.cuts[RT_MAX_PEERS] = n_items;
+    P.n_parts = n_parts; P.me = part;
+    float *local = (float *)h_slabs[part];
+    const int nt = (n_items + 31) / 32;
+    gram_pull_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+    RT_CHECK_LAUNCH();
+    if (!unpermute) return RT_OK;
+    RT_ARG(d_rank_of && d_orig_of && d_G && ldg >= n_items && d_G != local, "unpermute arguments");
+    return launch_unpermute(n_items, local, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
+}
+
 extern "C" int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
                               const int32_t *d_orig_of, float *d_G, int64_t ldg, void *stream) {
     RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items, "arguments");
@@ -391,16 +453,5 @@ extern "C" int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const 
     const int nt = (n_items + 31) / 32;
     gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
     RT_CHECK_LAUNCH();
-    const size_t row_bytes = sizeof(float) * (size_t)n_items;
-    const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
-    const size_t smem = stage ? row_bytes : 0;
-    RT_CUDA(cudaFuncSetAttribute(gram_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = stage ? (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024)) : 2;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
-    int grid = rt::sm_count() * per_sm;
-    if (grid > n_items) grid = n_items;
-    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
-    RT_CHECK_LAUNCH();
-    return RT_OK;
+    return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
 }

@@ -193,17 +193,41 @@ class GramLower:
     cuts: list        # row cut points, len n_parts + 1
 
 
-def gram_lower(X: DeviceMatrix, part: int = 0, n_parts: int = 1) -> GramLower:
+def gram_lower(X: DeviceMatrix, part: int = 0, n_parts: int = 1, raw_ptr: Optional[int] = None) -> GramLower:
+    """Row slab ``part`` of the rank-space lower triangle.  ``raw_ptr``: write into this raw device buffer
+    (I*I floats, e.g. a CUDA IPC buffer shared with the peer ranks) instead of a fresh torch tensor; the
+    returned ``Gp`` is then that integer address."""
     t = require_cuda()
+    lib = _lib.load()
     I = X.n_items
-    Gp = t.zeros((I, I), dtype=t.float32, device=dev())
+    if raw_ptr is None:
+        Gp = t.zeros((I, I), dtype=t.float32, device=dev())
+        gp_ptr = ptr(Gp)
+    else:
+        Gp = int(raw_ptr)
+        gp_ptr = C.c_void_p(Gp)
+        check(lib.rt_memset(gp_ptr, 0, 4 * I * I, stream_ptr()), "rt_memset")
     rank_of = empty(I, t.int32)
     orig_of = empty(I, t.int32)
     cuts = (C.c_int32 * (n_parts + 1))()
-    check(_lib.load().rt_gram_lower(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx),
-                                    ptr(X.rval), X.nnz, int(part), int(n_parts), ptr(Gp), I, ptr(rank_of), ptr(orig_of),
-                                    cuts, stream_ptr()), "rt_gram_lower")
+    check(lib.rt_gram_lower(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx),
+                            ptr(X.rval), X.nnz, int(part), int(n_parts), gp_ptr, I, ptr(rank_of), ptr(orig_of),
+                            cuts, stream_ptr()), "rt_gram_lower")
     return GramLower(Gp, rank_of, orig_of, list(cuts))
+
+
+def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: int, out=None):
+    """Fused slab exchange + mirror over peer memory, then the un-permuted symmetric G (rt_gram_finish_p2p).
+    ``slab_ptrs[p]``: address of rank p's slab buffer in this process (own buffer or IPC mapping)."""
+    t = require_cuda()
+    n_parts = len(slab_ptrs)
+    if out is None:
+        out = t.empty((n_items, n_items), dtype=t.float32, device=dev())
+    arr = (C.c_void_p * n_parts)(*[C.c_void_p(int(p)) for p in slab_ptrs])
+    cuts = (C.c_int32 * (n_parts + 1))(*[int(c) for c in L.cuts])
+    check(_lib.load().rt_gram_finish_p2p(n_items, arr, n_parts, int(part), cuts, n_items, ptr(L.rank_of), ptr(L.orig_of),
+                                         ptr(out), n_items, 1, stream_ptr()), "rt_gram_finish_p2p")
+    return out
 
 
 def gram_finish(L: GramLower, out=None):

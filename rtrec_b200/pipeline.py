@@ -84,6 +84,15 @@ def item_shard(n_items: int, rank: int, world: int, cptr_host: Optional[np.ndarr
     return (n_items * rank) // world, (n_items * (rank + 1)) // world
 
 
+def item_stride(n_items: int, rank: int, world: int):
+    """Interleaved target columns ``rank, rank + world, ...`` (device int32).  The cost of one solve grows
+    with the popularity of the target (more live candidates), and real item ids are often correlated with
+    popularity or age, so a stride balances the fit better than contiguous ranges.  Used when the scoring
+    side does not need contiguous column shards (query-partitioned scoring)."""
+    t = D.require_cuda()
+    return t.arange(rank, n_items, max(world, 1), dtype=t.int32, device=D.dev())
+
+
 def query_cuts(rptr, users, world: int) -> list:
     """Cut points (len world + 1) of the query list, balanced by the stored entries of the queried rows
     (the scoring work of a user grows with its row length).  Computed from replicated data, so every rank
@@ -122,9 +131,118 @@ def exchange_slabs(M, cuts, group=None):
         w.wait()
 
 
+class PeerSlabs:
+    """One I x I float32 slab buffer per rank, mapped into every rank of the node through CUDA IPC, plus the
+    stream-ordered barriers the fused exchange needs.  Buffers are cached per (group, n_items) and reused."""
+
+    _cache: dict = {}
+
+    def __init__(self, n_items: int, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        t = D.require_cuda()
+        lib = _lib.load()
+        self.n_items, self.rank, self.world, self.group = n_items, rank, world, group
+        self.own, self.ptrs, self.error = 0, [0] * world, None
+        self._flag = t.zeros(1, dtype=t.int32, device=D.dev())
+        # every rank takes part in both collectives below whatever happens locally, so a failure on one
+        # rank (IPC not permitted in this container, out of memory) turns into an agreed fallback, not a hang
+        payload = None
+        try:
+            own = C.c_void_p(0)
+            handle = (C.c_uint8 * 64)()
+            _lib.check(lib.rt_ipc_alloc(4 * n_items * n_items, C.byref(own), handle), "rt_ipc_alloc")
+            self.own = int(own.value)
+            payload = bytes(handle)
+        except Exception as e:  # noqa: BLE001
+            self.error = str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, payload, group=group)
+        if self.error is None and any(h is None for h in handles):
+            self.error = "a peer rank could not export its slab buffer"
+        if self.error is None:
+            try:
+                for r in range(world):
+                    if r == rank:
+                        self.ptrs[r] = self.own
+                        continue
+                    p = C.c_void_p(0)
+                    hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                    _lib.check(lib.rt_ipc_open(hb, C.byref(p)), "rt_ipc_open")
+                    self.ptrs[r] = int(p.value)
+            except Exception as e:  # noqa: BLE001
+                self.error = str(e)
+        ok = t.tensor([0 if self.error else 1], dtype=t.int32, device=D.dev())
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.error = self.error or "a peer rank could not map the slab buffers"
+            self.close()
+
+    @classmethod
+    def get(cls, n_items: int, rank: int, world: int, group=None) -> Optional["PeerSlabs"]:
+        """The node's slab buffers for this shape, or None when CUDA IPC is not usable here (agreed by all
+        ranks; the caller then exchanges the slabs with NCCL)."""
+        key = (id(group), n_items, rank, world)
+        if key not in cls._cache:
+            for k in [k for k in cls._cache if k[0] == key[0]]:
+                old = cls._cache.pop(k)
+                if old is not None:
+                    old.close()
+            obj = cls(n_items, rank, world, group)
+            cls._cache[key] = None if obj.error else obj
+            if obj.error and rank == 0:
+                import logging
+                logging.warning(f"peer-memory slab exchange unavailable ({obj.error}); using NCCL broadcasts")
+        return cls._cache[key]
+
+    def barrier(self) -> None:
+        """Stream-ordered node barrier: the one-element all-reduce completes only after every rank has
+        reached it on its stream."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self) -> None:
+        lib = _lib.load()
+        D.torch().cuda.synchronize()
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                lib.rt_ipc_close(C.c_void_p(p))
+        if self.own:
+            lib.rt_ipc_free(C.c_void_p(self.own))
+        self.ptrs, self.own = [], 0
+
+
+def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchange: str = "p2p", marks=None):
+    """Item-item Gram matrix on every rank of the node: each rank computes its row slab of the rank-space
+    lower triangle; ``exchange="p2p"`` pulls the other slabs over NVLink inside the mirror kernel
+    (rt_gram_finish_p2p), ``exchange="nccl"`` broadcasts the slabs and mirrors locally."""
+    mark = marks if marks is not None else (lambda name: None)
+    if world <= 1:
+        L = D.gram_lower(X)
+        mark("gram_lower")
+        G = D.gram_finish(L)
+        mark("gram_finish")
+        return G
+    slabs = PeerSlabs.get(X.n_items, rank, world, group) if exchange == "p2p" else None
+    if slabs is not None:
+        slabs.barrier()   # nobody is still reading the slab of the previous fit
+        L = D.gram_lower(X, part=rank, n_parts=world, raw_ptr=slabs.own)
+        mark("gram_lower")
+        slabs.barrier()   # every slab is complete
+        G = D.gram_finish_p2p(L, slabs.ptrs, rank, X.n_items)
+        mark("gram_finish_p2p")
+        return G
+    L = D.gram_lower(X, part=rank, n_parts=world)
+    mark("gram_lower")
+    exchange_slabs(L.Gp, L.cuts, group=group)
+    mark("gram_exchange")
+    G = D.gram_finish(L)
+    mark("gram_finish")
+    return G
+
+
 def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int = 1, group=None,
-                targets=None, want_sel: bool = False):
-    """Gram row slab of this rank -> all-gather of the slabs (NCCL) -> mirror/unpermute -> solve this rank's targets.
+                targets=None, want_sel: bool = False, strided: bool = False, exchange: str = "p2p"):
+    """Gram row slab of this rank -> slab exchange fused with the mirror (P2P) -> unpermute -> solve this rank's targets.
 
     Returns ``(res, (j0, j1))`` where ``res`` holds this rank's columns of W (``SolveResult``).
     With ``world == 1`` this is the single-GPU bulk fit.
@@ -132,16 +250,15 @@ def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int 
     t = D.require_cuda()
     I = X.n_items
     j0, j1 = item_shard(I, rank, world)
-    # K3: this rank's row slab of the rank-space lower triangle (rows balanced by multiply-add count)
-    L = D.gram_lower(X, part=rank, n_parts=world)
-    if world > 1:
-        exchange_slabs(L.Gp, L.cuts, group=group)
-    G = D.gram_finish(L)
-    del L
-    if targets is None:
-        tg = t.arange(j0, j1, dtype=t.int32, device=D.dev())
-    else:
+    # K3: this rank's row slab of the rank-space lower triangle (rows balanced by multiply-add count),
+    # exchanged over peer memory inside the mirror kernel
+    G = gram_sharded(X, rank=rank, world=world, group=group, exchange=exchange)
+    if targets is not None:
         tg = targets
+    elif strided and world > 1:
+        tg = item_stride(I, rank, world)
+    else:
+        tg = t.arange(j0, j1, dtype=t.int32, device=D.dev())
     res = D.solve(G, I, tg, cfg, want_sel=want_sel)
     del G
     return res, (j0, j1)

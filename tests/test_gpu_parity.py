@@ -125,6 +125,37 @@ def test_gram_v3_equals_model_and_shards(shuffle):
     assert np.abs(Gc - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+def test_gram_fused_pull_mirror_equals_single_pass():
+    """rt_gram_finish_p2p on one GPU: three slabs in three separate buffers (standing in for the IPC mappings
+    of peer ranks) are pulled, mirrored and un-permuted in one call; from every rank's point of view the
+    result is the single-pass Gram matrix, exactly.  Also covers the raw-buffer form of rt_gram_lower."""
+    import ctypes as C
+    from rtrec_b200 import _lib, device as D
+    lib = _lib.load()
+    U, I, N = 2500, 1777, 120000
+    u, i, ts, r = synth_events(U, I, N, seed=9, rating="int")
+    i = np.random.default_rng(2).permutation(I)[i]
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    dX = D.DeviceMatrix.from_scipy(X)
+    G_ref = D.gram_full(dX).cpu().numpy()
+    n_parts = 3
+    bufs, handles = [], []
+    try:
+        for p in range(n_parts):
+            ptr_, h = C.c_void_p(0), (C.c_uint8 * 64)()
+            _lib.check(lib.rt_ipc_alloc(4 * I * I, C.byref(ptr_), h), "rt_ipc_alloc")
+            bufs.append(int(ptr_.value))
+        parts = [D.gram_lower(dX, part=p, n_parts=n_parts, raw_ptr=bufs[p]) for p in range(n_parts)]
+        assert all(q.cuts == parts[0].cuts for q in parts)
+        for me in range(n_parts):
+            G = D.gram_finish_p2p(parts[me], bufs, me, I).cpu().numpy()
+            assert np.array_equal(G, G_ref), f"rank {me}"  # pulls only write outside the puller's own slab
+    finally:
+        D.torch().cuda.synchronize()
+        for b in bufs:
+            lib.rt_ipc_free(C.c_void_p(b))
+
+
 # ------------------------------------------------------------------------------------------ fit
 @pytest.mark.parametrize("name,cfg", FIT_CASES)
 def test_fit_matches_reference_golden(golden, name, cfg):
