@@ -421,7 +421,18 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
 
 static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
                             const int32_t *d_orig_of, float *d_G, int64_t ldg, cudaStream_t st) {
-    return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
+    const size_t row_bytes = sizeof(float) * (size_t)n_items;
+    const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
+    const size_t smem = stage ? row_bytes : 0;
+    RT_CUDA(cudaFuncSetAttribute(gram_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = stage ? (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024)) : 2;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int grid = rt::sm_count() * per_sm;
+    if (grid > n_items) grid = n_items;
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
 }
 
 extern "C" int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part,
