@@ -243,7 +243,11 @@ def run_ours(args):
         ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count()
     ms_t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    ms_ranks = [ms_total / args.steps]
     if world > 1:
+        all_ms = torch.empty(world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(all_ms, ms_t)
+        ms_ranks = [x / args.steps for x in all_ms.tolist()]
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_step = float(ms_t.item()) / args.steps
     value = U / (ms_step / 1e3)
@@ -334,7 +338,7 @@ def run_ours(args):
             "solver": {"mean_sweeps": round(float(stats[:, 0].mean()), 2), "mean_draws": round(float(stats[:, 1].mean()), 1),
                        "nnz_W": int(W.nnz)},
             "roofline": roofline, "kernels": other, "e2e": e2e, "cpu_baseline": cpu_baseline,
-            "gpu_launches": int(launches), "clocks": clk.summary(), "wall_s_timed_region": round(t_wall, 4),
+            "ms_per_step_ranks": [round(x, 3) for x in ms_ranks], "gpu_launches": int(launches), "clocks": clk.summary(), "wall_s_timed_region": round(t_wall, 4),
         }
         print(json.dumps(line))
     if world > 1:

@@ -256,7 +256,7 @@ struct GramPeers {
     int me;
 };
 
-__global__ void __launch_bounds__(256) gram_pull_mirror_kernel(GramPeers P, float *__restrict__ G, int n, int64_t ld) {
+__global__ void __launch_bounds__(256) gram_pull_mirror_kernel(GramPeers P, float *G, int n, int64_t ld) {
     __shared__ float tile[32][33];
     const int bx = blockIdx.x, by = blockIdx.y;
     if (bx > by) return;
@@ -277,6 +277,64 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_kernel(GramPeers P, floa
     for (int r = ty; r < 32; r += 8) {
         const int row = bx * 32 + r, col = by * 32 + tx;  // destination (upper)
         if (row < n && col < n && col > row) G[(size_t)row * ld + col] = tile[tx][r];
+    }
+}
+
+// Same with 64 x 64 tiles and 16-byte accesses (needs ld % 4 == 0 and 16-byte aligned slabs): NVLink P2P
+// reads reach their bandwidth only with wide loads and many bytes in flight (4 x LDG.128 per thread).
+__global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, float *G, int n, int64_t ld) {
+    __shared__ float tile[64][65];
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (bx > by) return;
+    const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;  // 16 threads cover the 64 columns of a row
+    float4 v[4];
+    int own[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int row = by * 64 + r0 + 16 * q, col = bx * 64 + c4;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        own[q] = P.me;
+        if (row < n && col <= row) {   // col <= row: the float4 starts inside the triangle (may run past the diagonal)
+            int owner = 0;
+#pragma unroll
+            for (int p = 1; p < RT_MAX_PEERS; ++p) owner += (p < P.n_parts && row >= P.cuts[p]) ? 1 : 0;
+            own[q] = owner;
+            v[q] = *reinterpret_cast<const float4 *>(P.src[owner] + (size_t)row * ld + col);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + 16 * q;
+        const int row = by * 64 + r, col = bx * 64 + c4;
+        // entries right of the diagonal inside a float4 are not part of the lower triangle: keep the local value
+        // out of the tile (the transposed store below only uses entries with col < row) and store only the
+        // in-triangle prefix locally
+        if (own[q] != P.me && row < n && col <= row) {
+            float *dst = G + (size_t)row * ld + col;
+            if (col + 3 <= row) *reinterpret_cast<float4 *>(dst) = v[q];
+            else {
+                dst[0] = v[q].x;
+                if (col + 1 <= row) dst[1] = v[q].y;
+                if (col + 2 <= row) dst[2] = v[q].z;
+            }
+        }
+        tile[r][c4 + 0] = v[q].x; tile[r][c4 + 1] = v[q].y; tile[r][c4 + 2] = v[q].z; tile[r][c4 + 3] = v[q].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int row = bx * 64 + r0 + 16 * q;       // destination row (upper triangle)
+        const int col = by * 64 + c4;                // destination columns col .. col+3
+        if (row >= n) continue;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = tile[c4 + e][r0 + 16 * q];
+        float *dst = G + (size_t)row * ld + col;
+        if (col > row && col + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e > row && col + e < n) dst[e] = o[e];
+        }
     }
 }
 
@@ -448,8 +506,15 @@ extern "C" int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, i
     P.cuts[RT_MAX_PEERS] = n_items;
     P.n_parts = n_parts; P.me = part;
     float *local = (float *)h_slabs[part];
-    const int nt = (n_items + 31) / 32;
-    gram_pull_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+    bool wide = (ldgp % 4) == 0;
+    for (int p = 0; p < n_parts; ++p) wide = wide && ((((uintptr_t)h_slabs[p]) & 15) == 0);
+    if (wide) {
+        const int nt = (n_items + 63) / 64;
+        gram_pull_mirror_v4_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+    } else {
+        const int nt = (n_items + 31) / 32;
+        gram_pull_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+    }
     RT_CHECK_LAUNCH();
     if (!unpermute) return RT_OK;
     RT_ARG(d_rank_of && d_orig_of && d_G && ldg >= n_items && d_G != local, "unpermute arguments");

@@ -193,25 +193,30 @@ class GramLower:
     cuts: list        # row cut points, len n_parts + 1
 
 
+def slab_ld(n_items: int) -> int:
+    """Leading dimension of a raw slab buffer: padded so that rows start 16-byte aligned (wide P2P loads)."""
+    return (int(n_items) + 3) // 4 * 4
+
+
 def gram_lower(X: DeviceMatrix, part: int = 0, n_parts: int = 1, raw_ptr: Optional[int] = None) -> GramLower:
     """Row slab ``part`` of the rank-space lower triangle.  ``raw_ptr``: write into this raw device buffer
-    (I*I floats, e.g. a CUDA IPC buffer shared with the peer ranks) instead of a fresh torch tensor; the
-    returned ``Gp`` is then that integer address."""
+    (I rows of ``slab_ld(I)`` floats, e.g. a CUDA IPC buffer shared with the peer ranks) instead of a fresh
+    torch tensor; the returned ``Gp`` is then that integer address."""
     t = require_cuda()
     lib = _lib.load()
     I = X.n_items
     if raw_ptr is None:
         Gp = t.zeros((I, I), dtype=t.float32, device=dev())
-        gp_ptr = ptr(Gp)
+        gp_ptr, ld = ptr(Gp), I
     else:
         Gp = int(raw_ptr)
-        gp_ptr = C.c_void_p(Gp)
-        check(lib.rt_memset(gp_ptr, 0, 4 * I * I, stream_ptr()), "rt_memset")
+        gp_ptr, ld = C.c_void_p(Gp), slab_ld(I)
+        check(lib.rt_memset(gp_ptr, 0, 4 * I * ld, stream_ptr()), "rt_memset")
     rank_of = empty(I, t.int32)
     orig_of = empty(I, t.int32)
     cuts = (C.c_int32 * (n_parts + 1))()
     check(lib.rt_gram_lower(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx),
-                            ptr(X.rval), X.nnz, int(part), int(n_parts), gp_ptr, I, ptr(rank_of), ptr(orig_of),
+                            ptr(X.rval), X.nnz, int(part), int(n_parts), gp_ptr, ld, ptr(rank_of), ptr(orig_of),
                             cuts, stream_ptr()), "rt_gram_lower")
     return GramLower(Gp, rank_of, orig_of, list(cuts))
 
@@ -225,8 +230,8 @@ def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: 
         out = t.empty((n_items, n_items), dtype=t.float32, device=dev())
     arr = (C.c_void_p * n_parts)(*[C.c_void_p(int(p)) for p in slab_ptrs])
     cuts = (C.c_int32 * (n_parts + 1))(*[int(c) for c in L.cuts])
-    check(_lib.load().rt_gram_finish_p2p(n_items, arr, n_parts, int(part), cuts, n_items, ptr(L.rank_of), ptr(L.orig_of),
-                                         ptr(out), n_items, 1, stream_ptr()), "rt_gram_finish_p2p")
+    check(_lib.load().rt_gram_finish_p2p(n_items, arr, n_parts, int(part), cuts, slab_ld(n_items), ptr(L.rank_of),
+                                         ptr(L.orig_of), ptr(out), n_items, 1, stream_ptr()), "rt_gram_finish_p2p")
     return out
 
 

@@ -150,7 +150,7 @@ class PeerSlabs:
         try:
             own = C.c_void_p(0)
             handle = (C.c_uint8 * 64)()
-            _lib.check(lib.rt_ipc_alloc(4 * n_items * n_items, C.byref(own), handle), "rt_ipc_alloc")
+            _lib.check(lib.rt_ipc_alloc(4 * n_items * D.slab_ld(n_items), C.byref(own), handle), "rt_ipc_alloc")
             self.own = int(own.value)
             payload = bytes(handle)
         except Exception as e:  # noqa: BLE001

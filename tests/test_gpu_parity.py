@@ -143,7 +143,7 @@ def test_gram_fused_pull_mirror_equals_single_pass():
     try:
         for p in range(n_parts):
             ptr_, h = C.c_void_p(0), (C.c_uint8 * 64)()
-            _lib.check(lib.rt_ipc_alloc(4 * I * I, C.byref(ptr_), h), "rt_ipc_alloc")
+            _lib.check(lib.rt_ipc_alloc(4 * I * D.slab_ld(I), C.byref(ptr_), h), "rt_ipc_alloc")
             bufs.append(int(ptr_.value))
         parts = [D.gram_lower(dX, part=p, n_parts=n_parts, raw_ptr=bufs[p]) for p in range(n_parts)]
         assert all(q.cuts == parts[0].cuts for q in parts)
