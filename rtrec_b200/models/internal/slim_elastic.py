@@ -56,6 +56,7 @@ class SLIMElastic:
         self._W_host: Optional[sp.csc_matrix] = None  # lazy mirror / pending upload
         self.last_fit_stats: Optional[np.ndarray] = None
         self.last_fit_sel: Optional[np.ndarray] = None
+        self.last_fit_targets: Optional[np.ndarray] = None
         self.keep_fit_details = bool(config.get("keep_fit_details", False))
 
     # ------------------------------------------------------------------ item_similarity mirror
@@ -117,6 +118,7 @@ class SLIMElastic:
         self._W_host = None
         if self.keep_fit_details:
             self.last_fit_stats = res.stats.cpu().numpy()
+            self.last_fit_targets = np.asarray(targets, dtype=np.int64).copy()
             self.last_fit_sel = res.sel.cpu().numpy() if res.sel is not None else None
         return self
 
