@@ -36,13 +36,43 @@ def column_errors(W_a, W_b, cols=None):
     return rel
 
 
-def assert_w_parity(W_a, W_b, cols=None, max_flip_frac=0.02, what="W"):
+def enet_objective(X_csc, j, w_col, alpha=0.1, l1_ratio=0.1):
+    """sklearn's ElasticNet objective of target column j for the coefficient vector ``w_col`` (dense, length
+    n_items), in float64: 0.5*||y - X_{-j} w||^2 + a*||w||_1 + 0.5*b*||w||^2 with a, b scaled by n_samples
+    (_coordinate_descent.py:781-782; column j of X is zeroed like slim_elastic.py:266)."""
+    n = X_csc.shape[0]
+    a, b = alpha * l1_ratio * n, alpha * (1.0 - l1_ratio) * n
+    X64 = X_csc.astype(np.float64)
+    y = np.asarray(X64[:, j].todense()).ravel()
+    w = np.asarray(w_col, dtype=np.float64).copy()
+    w[j] = 0.0
+    r = y - X64 @ w
+    return 0.5 * float(r @ r) + a * float(np.abs(w).sum()) + 0.5 * b * float(w @ w), float(y @ y)
+
+
+def assert_w_parity(W_a, W_b, cols=None, max_flip_frac=0.02, what="W", X=None, alpha=0.1, l1_ratio=0.1, tol=1e-4):
+    """W_a (device) against W_b (reference/oracle), column by column, error relative to the column's largest
+    coefficient: <= 1e-4 (north_star) on all but ``max_flip_frac`` of the columns.  The exceptions are columns
+    where the solver's stop test -- a comparison of the fp32 duality gap with tol*||y||^2, sensitive to
+    summation order even between two sklearn builds -- lets one side run a sweep longer.  They must agree to
+    1e-3, or, when the matrix ``X`` the columns were fitted on is given, both must be solutions sklearn
+    accepts: objective values within 1 % of tol*||y||^2 of each other (a hundred times tighter than the
+    solver's own stopping criterion on the duality gap)."""
     rel = column_errors(W_a, W_b, cols)
     n = len(list(cols)) if cols is not None else W_b.shape[1]
     bad = int((rel > W_TOL).sum())
     worst = float(rel.max()) if len(rel) else 0.0
-    assert worst <= W_TOL_FLIP, f"{what}: worst column error {worst:.3e} > {W_TOL_FLIP}"
     assert bad <= max(1, int(max_flip_frac * n)), f"{what}: {bad}/{n} columns above {W_TOL} (worst {worst:.3e})"
+    far = np.flatnonzero(rel > W_TOL_FLIP)
+    if len(far):
+        assert X is not None, f"{what}: worst column error {worst:.3e} > {W_TOL_FLIP}"
+        A = sp.csc_matrix(W_a, dtype=np.float64); B = sp.csc_matrix(W_b, dtype=np.float64)
+        Xc = sp.csc_matrix(X)
+        for j in far.tolist():
+            pa, yy = enet_objective(Xc, j, np.asarray(A[:, j].todense()).ravel(), alpha, l1_ratio)
+            pb, _ = enet_objective(Xc, j, np.asarray(B[:, j].todense()).ravel(), alpha, l1_ratio)
+            assert abs(pa - pb) <= 0.01 * tol * yy, (f"{what}: column {j} differs by {rel[j]:.3e} and the objectives "
+                                                     f"{pa:.9g} / {pb:.9g} differ by more than 0.01*tol*yy = {0.01 * tol * yy:.3g}")
     return rel
 
 

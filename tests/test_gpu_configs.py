@@ -92,7 +92,7 @@ def test_c4_like_streaming_partial_fit(force_identify):
     o = so.SlimOracle({"nn_feature_selection": nn, "n_threads": 8})
     X0 = so.state_to_matrix(state, fmt="csc")
     o.fit(X0, sel_in=m.model.last_fit_sel)
-    assert_w_parity(m.model.item_similarity, o.item_similarity, what="C4-like bulk")
+    assert_w_parity(m.model.item_similarity, o.item_similarity, what="C4-like bulk", X=X0)
     rng = np.random.default_rng(7)
     t_next = ts.max() + 1.0
     for b in range(2):
@@ -114,7 +114,7 @@ def test_c4_like_streaming_partial_fit(force_identify):
         assert _exact(m.interactions.to_csc(items.tolist()), X_sel)
         # SLIM.fit hands the recorded items in set order; the oracle solves the same set (column solves are independent)
         o.partial_fit_items(X_sel, items, sel_in=None if m.model.last_fit_sel is None else _sel_for(m, items))
-        assert_w_parity(m.model.item_similarity, o.item_similarity, cols=items, what=f"C4-like batch {b}")
+        assert_w_parity(m.model.item_similarity, o.item_similarity, cols=items, what=f"C4-like batch {b}", X=X_sel)
         untouched = np.setdiff1d(np.arange(I), items)
         W_after = m.model.item_similarity
         if len(untouched):
