@@ -425,8 +425,14 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
         const unsigned grid = (unsigned)(((int64_t)n_users * 32 + bs - 1) / bs);
         relabel_keys_kernel<<<grid, bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rank_of, P.keys);
         RT_CHECK_LAUNCH();
-        const int end_bit = 32 + bits_for_n(n_users);
-        G3_CUB(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys, P.keys2, d_rval, P.pval, (int)nnz, 0, end_bit, st));
+        // two stable sorts over the populated bit ranges (rank bits, then user bits) instead of one over
+        // [0, 32 + user bits): the zero bits in between would cost whole radix passes.  keys -> keys2 -> keys;
+        // cpos (written later by entry_pos_kernel) holds the intermediate values.
+        const int rank_bits = bits_for_n(n_items), user_bits = bits_for_n(n_users);
+        float *mid_v = (float *)P.cpos;
+        G3_CUB(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys, P.keys2, d_rval, mid_v, (int)nnz, 0, rank_bits, st));
+        G3_CUB(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys2, P.keys, mid_v, P.pval, (int)nnz, 32, 32 + user_bits, st));
+        { unsigned long long *t_ = P.keys; P.keys = P.keys2; P.keys2 = t_; }
         low32_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(P.keys2, nnz, P.pidx);
         RT_CHECK_LAUNCH();
     }

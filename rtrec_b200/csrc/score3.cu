@@ -149,7 +149,8 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                   const int *__restrict__ wridx, const float *__restrict__ wrval, const int *__restrict__ heavy_of,
                   const int *__restrict__ ell_off, const int2 *__restrict__ ell, int n_tiles, int n_items, int j_begin,
                   int j_end, int k, int filter, int mode, int tile, int *__restrict__ out_ids,
-                  float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ next_query) {
+                  float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ next_query,
+                  const int *__restrict__ order) {
     extern __shared__ __align__(16) float acc[];
     __shared__ Score3Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,8 +158,10 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
         __syncthreads();
         if (tid == 0) sh.q = atomicAdd(next_query, 1);
         __syncthreads();
-        const int q = sh.q;
-        if (q >= n_query) break;
+        if (sh.q >= n_query) break;
+        // queries are taken longest row first (order[] from the launcher): the dynamic queue then ends with the
+        // cheap users and no CTA is left alone with an expensive one
+        const int q = order ? order[sh.q] : sh.q;
         const int u = users[q];
         const int r0 = rptr[u], r1 = rptr[u + 1];
         int nbest = 0;
@@ -306,6 +309,16 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
     }
 }
 
+// sort key of a query: its row length (the scoring work grows with it)
+__global__ void query_len_kernel(const int *__restrict__ rptr, const int *__restrict__ users, int n_query,
+                                 unsigned *__restrict__ keys, int *__restrict__ idx) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_query) return;
+    const int u = users[q];
+    keys[q] = (unsigned)(rptr[u + 1] - rptr[u]);
+    idx[q] = q;
+}
+
 // tile geometry shared by the pack builder and the launcher: two CTAs per SM share the shared memory
 static void score3_geometry(int width, int *tile, int *n_tiles) {
     const int optin = rt::smem_optin();
@@ -433,9 +446,23 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_query) grid = n_query;
+    const int *d_order = nullptr;
+    if (n_query > 4 * grid) {
+        // longest-row-first processing order
+        const size_t nq = (size_t)n_query;
+        unsigned *keys = (unsigned *)rt::scratch(SCR_SCORE, (4 * nq + 256) * sizeof(int));
+        if (!keys) return RT_ERR_CUDA;
+        unsigned *keys2 = keys + nq + 32;
+        int *idx = (int *)(keys2 + nq + 32), *idx2 = idx + nq + 32;
+        query_len_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(d_rptr, d_users, n_query, keys, idx);
+        RT_CHECK_LAUNCH();
+        S3_CUB(cub::DeviceRadixSort::SortPairsDescending(d_tmp__, tmp_bytes__, keys, keys2, idx, idx2, n_query, 0, 32, st));
+        d_order = idx2;
+    }
     recommend3_kernel<<<grid, S3_NT, smem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval,
                                                 d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles, n_items, j_begin, j_end,
-                                                k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next);
+                                                k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next,
+                                                d_order);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

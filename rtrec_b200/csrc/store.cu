@@ -27,24 +27,36 @@ struct MaxOpD {
 
 __global__ void prep_events_kernel(const int *users, const int *items, const double *ts, int64_t n, double max_ts_in,
                                    unsigned long long *keys, unsigned *order, double *tplus, int *max_ui) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride: the id maxima are reduced per thread, per warp and per block, so the whole launch issues two
+    // atomics per block instead of two per warp on the same address (that serialisation was 1 ms at 20M events)
+    __shared__ int s_mu[32], s_mi[32];
     int mu = 0, mi = 0;
-    if (k < n) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const int u = users[k], i = items[k];
         keys[k] = (((unsigned long long)(unsigned)u) << 32) | (unsigned)i;
         order[k] = (unsigned)k;
         double t = ts[k] + 1.0;
         if (k == 0 && max_ts_in > t) t = max_ts_in;
         tplus[k] = t;
-        mu = u; mi = i;
+        mu = max(mu, u); mi = max(mi, i);
     }
-    // block max of ids -> global atomicMax
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mu = max(mu, __shfl_xor_sync(0xffffffffu, mu, o));
         mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
     }
-    if ((threadIdx.x & 31) == 0) { atomicMax(&max_ui[0], mu); atomicMax(&max_ui[1], mi); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_mu[warp] = mu; s_mi[warp] = mi; }
+    __syncthreads();
+    if (warp == 0) {
+        mu = lane < nw ? s_mu[lane] : 0; mi = lane < nw ? s_mi[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mu = max(mu, __shfl_xor_sync(0xffffffffu, mu, o));
+            mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+        }
+        if (lane == 0) { atomicMax(&max_ui[0], mu); atomicMax(&max_ui[1], mi); }
+    }
 }
 
 __device__ __forceinline__ int64_t lower_bound_u64(const unsigned long long *a, int64_t n, unsigned long long v) {
@@ -274,8 +286,12 @@ extern "C" int rt_store_fold(const int32_t *d_users, const int32_t *d_items, con
     const unsigned gn = (unsigned)((n + bs - 1) / bs);
     int init_max[4] = {max_user_in, max_item_in, 0, 0};
     RT_CUDA(cudaMemcpyAsync(P.max_ui, init_max, sizeof(init_max), cudaMemcpyHostToDevice, st));
-    prep_events_kernel<<<gn, bs, 0, st>>>(d_users, d_items, d_ts, n, max_ts_in, (unsigned long long *)P.keys, P.order,
-                                         P.tplus, P.max_ui);
+    {
+        unsigned gp = (unsigned)rt::sm_count() * 8u;
+        if (gp > gn) gp = gn;
+        prep_events_kernel<<<gp, bs, 0, st>>>(d_users, d_items, d_ts, n, max_ts_in, (unsigned long long *)P.keys, P.order,
+                                             P.tplus, P.max_ui);
+    }
     RT_CHECK_LAUNCH();
     // T_k = inclusive running max of (ts+1)
     CUB_CALL(cub::DeviceScan::InclusiveScan(d_tmp__, tmp_bytes__, P.tplus, P.T, MaxOpD(), (int)n, st));
@@ -283,8 +299,16 @@ extern "C" int rt_store_fold(const int32_t *d_users, const int32_t *d_items, con
     int host_max[4];
     RT_CUDA(cudaMemcpyAsync(host_max, P.max_ui, sizeof(host_max), cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaStreamSynchronize(st));
-    const int end_bit = 32 + bits_for64((long long)host_max[0] + 1);
-    CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys, P.skeys, P.order, P.sorder, (int)n, 0, end_bit, st));
+    // stable LSD sort over the two populated bit ranges only (item bits, then user bits): bits between the
+    // largest item id and bit 32 are zero and would cost whole passes.  ukeys / isnew_i+new_rank serve as the
+    // intermediate buffers (they are written later).
+    {
+        const int item_bits = bits_for64((long long)host_max[1] + 1), user_bits = bits_for64((long long)host_max[0] + 1);
+        unsigned long long *mid_k = P.ukeys;
+        unsigned *mid_o = (unsigned *)P.old_pos;  // int64[n] scratch, large enough for n uint32
+        CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.keys, mid_k, P.order, mid_o, (int)n, 0, item_bits, st));
+        CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, mid_k, P.skeys, mid_o, P.sorder, (int)n, 32, 32 + user_bits, st));
+    }
     CUB_CALL(cub::DeviceRunLengthEncode::Encode(d_tmp__, tmp_bytes__, P.skeys, P.ukeys, P.run_len, P.n_runs, (int)n, st));
     int n_runs = 0;
     RT_CUDA(cudaMemcpyAsync(&n_runs, P.n_runs, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -386,8 +410,9 @@ extern "C" int rt_store_build(const uint64_t *d_keys, const double *d_vals, cons
         // CSC: sort by (item, user)
         swap_halves_kernel<<<gz, bs, 0, st>>>(keys, nnz, P.sw);
         RT_CHECK_LAUNCH();
+        // the entries arrive (user, item)-sorted, so a STABLE sort on the item bits alone yields (item, user) order
         const int end_bit = 32 + bits_for64(n_items);
-        CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.sw, P.sws, x, d_cval, (int)nnz, 0, end_bit, st));
+        CUB_CALL(cub::DeviceRadixSort::SortPairs(d_tmp__, tmp_bytes__, P.sw, P.sws, x, d_cval, (int)nnz, 32, end_bit, st));
         split_keys_kernel<<<gz, bs, 0, st>>>(P.sws, nnz, d_ccol, d_cidx);
         RT_CHECK_LAUNCH();
     }
