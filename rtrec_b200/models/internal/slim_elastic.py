@@ -14,6 +14,7 @@ There is no CPU path: without a GPU these methods raise ``RtrecB200Error``.
 """
 from __future__ import annotations
 
+import gc
 import logging
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -256,13 +257,21 @@ class SLIMElastic:
             pending.append((a, b, ev))
         out: List[List[int]] = []
         ids_np, cnt_np = h_ids.numpy(), h_cnt.numpy()
-        for a, b, ev in pending:
-            ev.synchronize()
-            rows = ids_np[a:b].tolist()
-            c = cnt_np[a:b]
-            for r in np.flatnonzero(c < k).tolist():  # lists shorter than k: drop the -1 padding
-                del rows[r][int(c[r]):]
-            out.extend(rows)
+        # a million small lists and ints are created below and none of them can be part of a cycle: keep the
+        # cyclic collector from rescanning the growing result while it is being built
+        gc_on = gc.isenabled()
+        gc.disable()
+        try:
+            for a, b, ev in pending:
+                ev.synchronize()
+                rows = ids_np[a:b].tolist()
+                c = cnt_np[a:b]
+                for r in np.flatnonzero(c < k).tolist():  # lists shorter than k: drop the -1 padding
+                    del rows[r][int(c[r]):]
+                out.extend(rows)
+        finally:
+            if gc_on:
+                gc.enable()
         return out
 
     def __getstate__(self):

@@ -69,7 +69,7 @@ class SLIM(BaseModel):
                              users_tags: Optional[List[List[str]]] = None, top_k: int = 10,
                              filter_interacted: bool = True) -> List[List[int]]:
         """slim.py:81-104: ``dense_output`` follows the id kind (ints -> sparse top-k semantics)."""
-        if self.model.item_similarity is None and self.model._W is None:
+        if self.model._W is None and self.model._W_host is None:  # (not .item_similarity: that would download W)
             raise RuntimeError("Model must be fitted before calling batch_recommend.")
         if len(user_ids) == 0:
             return []
