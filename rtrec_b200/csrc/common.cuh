@@ -13,12 +13,12 @@ void count_launch(int n = 1);
 int sm_count();
 int smem_optin();
 // tuning switches settable through rt_set_option(): which kernel generation serves an entry point
-enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_COUNT };
+enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_SOLVE_IMPL, OPT_COUNT };
 int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).
 void *scratch(int slot, size_t bytes);
-enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SLOTS };
+enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_SLOTS };
 
 #define RT_CUDA(expr)                                                                              \
     do {                                                                                           \

@@ -43,6 +43,8 @@ struct SolveArgs {
     int *stats;
     char *scratch;
     size_t scratch_per_cta;
+    const int *only_flagged;  // when set, the block kernel solves only targets t with only_flagged[t] != 0
+    int flag_mod;             // test hook (solve_impl = 3): the warp kernel hands every flag_mod-th target to the block kernel
     int hot_in_smem;  // per-visit arrays live in dynamic shared memory
     int use_gs;       // dense live x live Gram block cached in shared memory (nn mode)
 };
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
         __syncthreads();
         const int t = ms.t;
         if (t >= A.n_targets) break;
+        if (A.only_flagged && !A.only_flagged[t]) continue;
         const int j = A.targets[t];
         const float *gj = G + (size_t)j * ld;
 
@@ -421,6 +424,410 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
     }
 }
 
+
+// ================================================================================================
+// Warp-per-column solver (nn mode, universe <= 64 candidates).
+//
+// Same algorithm and the same arithmetic per coordinate visit as slim_solve_kernel; what changes is who
+// does it.  The block kernel spends 41 % of its time waiting on the two streaming passes of the target's
+// Gram row (128 threads, one 4-byte load each per step) and 29 % at CTA barriers while warp 0 walks the
+// draw sequence (profiles/r1l_*).  With nn <= 64 every per-column vector (universe, live set, w, h) has at
+// most two elements per lane, so ONE warp can own a column end to end: no CTA barrier anywhere, sixteen
+// columns in flight per SM instead of eight, and the row is streamed with 16-byte loads, eight in flight
+// per lane.  Candidate selection keeps the threshold idea of block_top_n_fast (128 strided bucket maxima ->
+// lower bound T of the n-th largest score -> collect everything >= T -> rank sort), with the bucket maxima
+// in registers (four per lane) and comparisons in the float domain.  Columns whose candidate list would
+// overflow (more than 512 scores above T) are flagged and solved by the block kernel afterwards.
+constexpr int SW_MAXU = 64;
+constexpr int SW_LIST = 512;
+
+struct WarpScratch {           // carved per warp out of dynamic shared memory
+    double w[SW_MAXU], h[SW_MAXU];
+    float qv[SW_MAXU], n2[SW_MAXU], xta[SW_MAXU];
+    int feat[SW_MAXU], live[SW_MAXU], live_slot[SW_MAXU], active[SW_MAXU], list[SW_MAXU];
+    unsigned char excl[SW_MAXU];
+    // followed by max(SW_LIST * 8, NU * NU * 4) bytes: candidate list during selection, then the live x live Gram block
+};
+
+__device__ __forceinline__ float sw_key_to_float(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ void sw_zero_at(float4 &v, int d) {   // v[d] = 0 without dynamic register indexing
+    v.x = d == 0 ? 0.0f : v.x; v.y = d == 1 ? 0.0f : v.y; v.z = d == 2 ? 0.0f : v.z; v.w = d == 3 ? 0.0f : v.w;
+}
+
+// ordered compaction inside a warp: returns the slot of this lane's element (valid iff flag) and adds the total to *count
+__device__ __forceinline__ int sw_compact(bool flag, int lane, int &count) {
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int pos = count + __popc(bal & ((1u << lane) - 1u));
+    count += __popc(bal);
+    return pos;
+}
+
+__global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, int *__restrict__ need_block, int per_warp_bytes) {
+    extern __shared__ __align__(16) char sw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    char *base = sw_smem + (size_t)warp * per_warp_bytes;
+    WarpScratch *S = (WarpScratch *)base;
+    char *tail = base + ((sizeof(WarpScratch) + 15) & ~(size_t)15);
+    uint32_t *lkey = (uint32_t *)tail;
+    int *lidx = (int *)(tail + sizeof(uint32_t) * SW_LIST);
+    float *Gs = (float *)tail;
+    const int NU = A.NU;
+    const double a = A.a, b = A.b;
+    const float *G = A.G;
+    const int64_t ld = A.ldg;
+    const int N = A.n_items;
+    const bool vec4 = ((ld & 3) == 0) && ((((uintptr_t)G) & 15) == 0);
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(&A.cursor[1], 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= A.n_targets) break;
+        const int j = A.targets[t];
+        const float *gj = G + (size_t)j * ld;
+        __syncwarp();
+
+        // ---- candidates ------------------------------------------------------------------------------
+        bool overflow = A.flag_mod > 0 && (t % A.flag_mod) == 0;
+        if (overflow) {
+        } else if (A.sel_in) {
+            for (int k = lane; k < NU; k += 32) S->feat[k] = A.sel_in[(size_t)t * A.nn + k];
+        } else {
+            // pass 1: 128 bucket maxima, bucket = (lane, index & 3); score of the target itself is 0
+            float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            const int N4 = vec4 ? (N >> 2) : 0;
+            {
+                int q = lane;
+                for (; q + 7 * 32 < N4; q += 8 * 32) {
+                    float4 v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r] = __ldg(reinterpret_cast<const float4 *>(gj) + q + 32 * r);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int i0 = (q + 32 * r) << 2;
+                        sw_zero_at(v[r], j - i0);
+                        bm[0] = fmaxf(bm[0], v[r].x); bm[1] = fmaxf(bm[1], v[r].y);
+                        bm[2] = fmaxf(bm[2], v[r].z); bm[3] = fmaxf(bm[3], v[r].w);
+                    }
+                }
+                for (; q < N4; q += 32) {
+                    float4 v = __ldg(reinterpret_cast<const float4 *>(gj) + q);
+                    const int i0 = q << 2;
+                    sw_zero_at(v, j - i0);
+                    bm[0] = fmaxf(bm[0], v.x); bm[1] = fmaxf(bm[1], v.y); bm[2] = fmaxf(bm[2], v.z); bm[3] = fmaxf(bm[3], v.w);
+                }
+                for (int i = (N4 << 2) + lane; i < N; i += 32) {
+                    const float v = i == j ? 0.0f : gj[i];
+                    const int c = i & 3;
+                    bm[0] = c == 0 ? fmaxf(bm[0], v) : bm[0]; bm[1] = c == 1 ? fmaxf(bm[1], v) : bm[1];
+                    bm[2] = c == 2 ? fmaxf(bm[2], v) : bm[2]; bm[3] = c == 3 ? fmaxf(bm[3], v) : bm[3];
+                }
+            }
+            const int kk = min(NU, N);
+            // T = kk-th largest bucket maximum (as an order-preserving key), by bitwise search
+            uint32_t bk[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bk[c] = bm[c] == -INFINITY ? 0u : float_key(bm[c]);
+            uint32_t T = 0u;
+            for (int bit = 31; bit >= 0; --bit) {
+                const uint32_t cand = T | (1u << bit);
+                int cnt = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cnt += __popc(__ballot_sync(0xffffffffu, bk[c] >= cand));
+                if (cnt >= kk) T = cand;
+            }
+            if (T == 0u) T = 1u;
+            const float Tf = T > 1u ? sw_key_to_float(T) : -INFINITY;
+            // pass 2: collect every score >= T (list order is irrelevant: it is rank-sorted below)
+            int total = 0, n_gt = 0;
+            auto visit = [&](int i, float v, bool strict, bool valid) {
+                const bool gt = valid && v > Tf;
+                const bool take = valid && (strict ? gt : (v >= Tf));
+                const unsigned bal = __ballot_sync(0xffffffffu, take);
+                if (bal) {
+                    const int pos = total + __popc(bal & ((1u << lane) - 1u));
+                    if (take && pos < SW_LIST) { lkey[pos] = float_key(v); lidx[pos] = i; }
+                    total += __popc(bal);
+                    n_gt += __popc(__ballot_sync(0xffffffffu, gt));
+                }
+            };
+            auto scan = [&](bool strict) {
+                total = 0; n_gt = 0;
+                int q = lane;
+                const int N4r = ((N4 + 31) / 32) * 32;   // whole-warp iterations (ballots inside)
+                for (; q < N4r; q += 32) {
+                    float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                    const int i0 = q << 2;
+                    if (q < N4) {
+                        v = __ldg(reinterpret_cast<const float4 *>(gj) + q);
+                        sw_zero_at(v, j - i0);
+                    }
+                    const bool ok = q < N4;
+                    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+                    if (__any_sync(0xffffffffu, ok && (strict ? (m4 > Tf) : (m4 >= Tf)))) {
+                        visit(i0 + 0, v.x, strict, ok); visit(i0 + 1, v.y, strict, ok);
+                        visit(i0 + 2, v.z, strict, ok); visit(i0 + 3, v.w, strict, ok);
+                    }
+                }
+                for (int base_i = (N4 << 2); base_i < N; base_i += 32) {
+                    const int i = base_i + lane;
+                    const float v = i < N ? (i == j ? 0.0f : gj[i]) : -INFINITY;
+                    visit(i, v, strict, i < N);
+                }
+            };
+            scan(false);
+            if (total > SW_LIST) {
+                const int c_gt = n_gt;
+                if (c_gt > SW_LIST) overflow = true;
+                else {
+                    __syncwarp();
+                    scan(true);                      // strictly larger ones only: exactly c_gt entries
+                    if (c_gt < kk) {
+                        // the remaining picks are the scores == T with the largest indices: scan downwards
+                        const int need = kk - c_gt;
+                        int taken = 0;
+                        for (int top = ((N + 31) / 32) * 32; top > 0 && taken < need; top -= 32) {
+                            const int x = top - 1 - lane;
+                            const float v = x < N ? (x == j ? 0.0f : gj[x]) : -INFINITY;
+                            const bool eq = x < N && v == Tf;
+                            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+                            const int pos = taken + __popc(bal & ((1u << lane) - 1u));
+                            if (eq && pos < need) { lkey[c_gt + pos] = T; lidx[c_gt + pos] = x; }
+                            taken += __popc(bal);
+                        }
+                        total = kk;
+                    } else total = c_gt;
+                }
+            }
+            if (!overflow) {
+                __syncwarp();
+                // rank sort by (key desc, index desc); the first kk ranks are the candidates in pick order
+                for (int e = lane; e < total; e += 32) {
+                    const uint32_t ke = lkey[e];
+                    const int ie = lidx[e];
+                    int rank = 0;
+                    for (int f = 0; f < total; ++f) {
+                        const uint32_t kf = lkey[f];
+                        const int jf = lidx[f];
+                        rank += (kf > ke) || (kf == ke && jf > ie);
+                    }
+                    if (rank < kk) S->feat[rank] = ie;
+                }
+            }
+        }
+        if (overflow) {
+            if (lane == 0) need_block[t] = 1;
+            continue;
+        }
+        __syncwarp();
+        if (A.sel_out) {
+            for (int k = lane; k < A.nn; k += 32) A.sel_out[(size_t)t * A.nn + k] = k < NU ? S->feat[k] : -1;
+        }
+
+        const double yy = (double)gj[j];
+        const double tol_abs = A.d_w_tol * yy;
+
+        // ---- live set (ordered compaction over the universe) ---------------------------------------------
+        int m = 0;
+        for (int base_k = 0; base_k < NU; base_k += 32) {
+            const int k = base_k + lane;
+            bool is_live = false;
+            float qk = 0.f, nk = 0.f;
+            if (k < NU) {
+                const int f = S->feat[k];
+                if (f != j) { qk = gj[f]; nk = A.diag[f]; }
+                is_live = nk > 0.f && (!(A.positive && A.nonneg) || (double)qk > a);
+            }
+            const int s = sw_compact(is_live, lane, m);
+            if (k < NU) {
+                if (is_live) { S->live_slot[k] = s; S->live[s] = k; S->w[s] = 0.0; S->h[s] = 0.0; S->qv[s] = qk; S->n2[s] = nk; }
+                else S->live_slot[k] = -1;
+            }
+        }
+        __syncwarp();
+        // live x live Gram block (symmetric: load the lower triangle, store both halves)
+        for (int e = lane; e < m * m; e += 32) {
+            const int r = e / m, c = e - r * m;
+            if (c <= r) {
+                const float v = G[(size_t)S->feat[S->live[r]] * ld + S->feat[S->live[c]]];
+                Gs[r * m + c] = v;
+                Gs[c * m + r] = v;
+            }
+        }
+        __syncwarp();
+
+        int n_active = 0, n_iter = 0, n_gap = 0, draws = 0;
+        double gap = 0.0, dual_norm = 0.0;
+
+        auto eval_gap = [&]() {
+            double wq = 0, wh = 0, l1 = 0, l2 = 0;
+            for (int s = lane; s < m; s += 32) {
+                const double ws = S->w[s];
+                wq += ws * (double)S->qv[s]; wh += ws * S->h[s]; l1 += fabs(ws); l2 += ws * ws;
+            }
+            wq = warp_sum(wq); wh = warp_sum(wh); l1 = warp_sum(l1); l2 = warp_sum(l2);
+            int ns = 0;
+            for (int base_s = 0; base_s < m; base_s += 32) {
+                const int s = base_s + lane;
+                const bool nz = s < m && S->w[s] != 0.0;
+                const int pos = sw_compact(nz, lane, ns);
+                if (nz) S->list[pos] = s;
+            }
+            __syncwarp();
+            double dn = -INFINITY;
+            for (int k = lane; k < NU; k += 32) {
+                const int s = S->live_slot[k];
+                double v;
+                if (s >= 0) v = (double)S->qv[s] - S->h[s] - b * S->w[s];
+                else {
+                    const int f = S->feat[k];
+                    if (f == j) v = 0.0;
+                    else {
+                        double hk = 0.0;
+                        for (int e = 0; e < ns; ++e) {
+                            const int sc = S->list[e];
+                            hk += (double)G[(size_t)S->feat[S->live[sc]] * ld + f] * S->w[sc];
+                        }
+                        v = (double)gj[f] - hk;
+                    }
+                }
+                S->xta[k] = (float)v;
+                dn = fmax(dn, A.positive ? v : fabs(v));
+            }
+            dn = warp_max(dn);
+            const double Rn = yy - 2.0 * wq + wh, Ry = yy - wq;
+            const double primal = 0.5 * (Rn + b * l2) + a * l1;
+            const double scale = dn > a ? a / dn : 1.0;
+            const double dualv = -0.5 * scale * scale * (Rn + b * l2) + scale * Ry;
+            gap = primal - dualv; dual_norm = dn;
+            ++n_gap;
+            __syncwarp();
+        };
+
+        auto screen = [&](bool first) {
+            const double denom = a > dual_norm ? a : dual_norm;
+            const double thr = sqrt(2.0 * gap) / a;
+            int na = 0, nd = 0;
+            for (int base_k = 0; base_k < NU; base_k += 32) {
+                const int k = base_k + lane;
+                bool keep = false, drop = false;
+                if (k < NU) {
+                    const int s = S->live_slot[k];
+                    const int f = S->feat[k];
+                    const double nk = s >= 0 ? (double)S->n2[s] : (f == j ? 0.0 : (double)A.diag[f]);
+                    bool consider;
+                    if (first) { consider = nk != 0.0; if (!consider) S->excl[k] = 1; }
+                    else consider = !S->excl[k];
+                    if (consider) {
+                        const double theta = (double)S->xta[k] / denom;
+                        const double dk = (1.0 - fabs(theta)) / sqrt(nk + b);
+                        if (dk <= thr) { keep = true; S->excl[k] = 0; }
+                        else { S->excl[k] = 1; drop = (s >= 0 && S->w[s] != 0.0); }
+                    }
+                }
+                const int pk = sw_compact(keep, lane, na);
+                const int pd = sw_compact(drop, lane, nd);
+                if (keep) S->active[pk] = k;
+                if (drop) S->list[pd] = S->live_slot[k];
+            }
+            __syncwarp();
+            for (int e = 0; e < nd; ++e) {
+                const int sc = S->list[e];
+                const double wsc = S->w[sc];
+                for (int r = lane; r < m; r += 32) S->h[r] -= wsc * (double)Gs[r * m + sc];
+                __syncwarp();
+                if (lane == 0) S->w[sc] = 0.0;
+                __syncwarp();
+            }
+            n_active = na;
+        };
+
+        eval_gap();
+        bool done = gap <= tol_abs;
+        if (!done && m == 0) { done = true; n_iter = A.max_iter; }
+        if (!done) {
+            screen(true);
+            int64_t tdraw = 0;
+            for (int it = 0; it < A.max_iter; ++it) {
+                int v = 0;
+                double wmax_l = 0.0, dwmax_l = 0.0;
+                while (v < n_active) {
+                    const int nb = min(32, n_active - v);
+                    bool upd = false;
+                    int s = -1;
+                    double wc = 0.0, wn = 0.0;
+                    if (lane < nb) {
+                        const uint32_t r = A.rng[tdraw + lane];
+                        const int k = S->active[r % (uint32_t)n_active];
+                        s = S->live_slot[k];
+                        if (s >= 0) {
+                            wc = S->w[s];
+                            const double nk = (double)S->n2[s];
+                            const double tmp = (double)S->qv[s] - S->h[s] + wc * nk;
+                            if (A.positive && tmp < 0.0) wn = 0.0;
+                            else {
+                                double mag = fabs(tmp) - a;
+                                if (!(mag > 0.0)) mag = 0.0;
+                                wn = (tmp > 0.0 ? mag : (tmp < 0.0 ? -mag : 0.0)) / (nk + b);
+                            }
+                            upd = wn != wc;
+                        }
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, upd);
+                    if (mask == 0u) {
+                        wmax_l = fmax(wmax_l, fabs(wn));
+                        v += nb; tdraw += nb;
+                        continue;
+                    }
+                    const int L0 = __ffs(mask) - 1;
+                    if (lane <= L0) wmax_l = fmax(wmax_l, fabs(wn));
+                    if (lane == L0) dwmax_l = fmax(dwmax_l, fabs(wn - wc));
+                    v += L0 + 1; tdraw += L0 + 1;
+                    // apply the first changing visit of the batch
+                    const int sc = __shfl_sync(0xffffffffu, s, L0);
+                    const double d = __shfl_sync(0xffffffffu, wn - wc, L0);
+                    const double wnew = __shfl_sync(0xffffffffu, wn, L0);
+                    for (int r = lane; r < m; r += 32) S->h[r] += d * (double)Gs[r * m + sc];
+                    if (lane == 0) S->w[sc] = wnew;
+                    __syncwarp();
+                }
+                draws += n_active;
+                n_iter = it + 1;
+                const double w_max = warp_max(wmax_l), d_w_max = warp_max(dwmax_l);
+                if (w_max == 0.0 || d_w_max / w_max <= A.d_w_tol || it == A.max_iter - 1) {
+                    eval_gap();
+                    if (gap <= tol_abs) break;
+                    screen(false);
+                }
+            }
+        }
+
+        // ---- output ------------------------------------------------------------------------------------
+        if (A.stats && lane == 0) {
+            A.stats[(size_t)t * 4 + 0] = n_iter; A.stats[(size_t)t * 4 + 1] = draws;
+            A.stats[(size_t)t * 4 + 2] = n_gap; A.stats[(size_t)t * 4 + 3] = m;
+        }
+        const int64_t off = (int64_t)t * NU;
+        for (int k = lane; k < NU; k += 32) {
+            const int s = S->live_slot[k];
+            A.out_rows[off + k] = S->feat[k];
+            A.out_vals[off + k] = s >= 0 ? (float)S->w[s] : 0.0f;
+        }
+        if (lane == 0) { A.out_off[t] = off; A.out_cnt[t] = NU; }
+    }
+}
+
+__global__ void count_flags_kernel(const int *__restrict__ flags, int n, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = i < n ? (flags[i] != 0) : 0;
+    v = warp_sum_i(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
+
 __global__ void gather_diag_kernel(const float *G, int64_t ld, int n, float *diag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) diag[i] = G[(size_t)i * ld + i];
@@ -560,12 +967,48 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
     A.scratch = (char *)d_workspace + 1024 + diag_bytes;
     A.scratch_per_cta = p.scratch_per_cta;
     A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
+    A.only_flagged = nullptr;
+    A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;
     RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
     gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(d_G, ldg, n_items, d_diag);
     RT_CHECK_LAUNCH();
-    RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-    slim_solve_kernel<<<p.grid, p.NT, p.smem_bytes, st>>>(A);
-    RT_CHECK_LAUNCH();
+    bool block_pass = true;
+    if (cfg->nn > 0 && p.NU <= SW_MAXU && rt::option(rt::OPT_SOLVE_IMPL) != 1) {
+        // warp-per-column kernel; columns it cannot take (candidate-list overflow) are flagged for the block kernel
+        const size_t tail = (size_t)SW_LIST * 8 > (size_t)p.NU * p.NU * 4 ? (size_t)SW_LIST * 8 : (size_t)p.NU * p.NU * 4;
+        const int per_warp = (int)(((sizeof(WarpScratch) + 15) & ~(size_t)15) + ((tail + 15) & ~(size_t)15));
+        int warps = (rt::smem_optin() - 1024) / per_warp;
+        if (warps > 16) warps = 16;
+        if (warps >= 4) {
+            int *d_flags = (int *)rt::scratch(SCR_SOLVE_FLAGS, sizeof(int) * ((size_t)n_targets + 64));
+            if (!d_flags) return RT_ERR_CUDA;
+            RT_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(int) * ((size_t)n_targets + 1), st));
+            const size_t smem = (size_t)warps * per_warp;
+            RT_CUDA(cudaFuncSetAttribute(slim_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int grid = rt::sm_count();
+            const int want = (n_targets + warps - 1) / warps;
+            if (grid > want) grid = want;
+            slim_solve_warp_kernel<<<grid, warps * 32, smem, st>>>(A, d_flags, per_warp);
+            RT_CHECK_LAUNCH();
+            // any flagged column?  (the flags are summed on the device; one int comes back)
+            int *d_nflag = d_flags + n_targets;
+            count_flags_kernel<<<(n_targets + 255) / 256, 256, 0, st>>>(d_flags, n_targets, d_nflag);
+            RT_CHECK_LAUNCH();
+            int n_flag = 0;
+            RT_CUDA(cudaMemcpyAsync(&n_flag, d_nflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            RT_CUDA(cudaStreamSynchronize(st));
+            block_pass = n_flag > 0;
+            if (block_pass) {
+                A.only_flagged = d_flags;
+                RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));  // reset the target cursor
+            }
+        }
+    }
+    if (block_pass) {
+        RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        slim_solve_kernel<<<p.grid, p.NT, p.smem_bytes, st>>>(A);
+        RT_CHECK_LAUNCH();
+    }
     unsigned long long cur[2] = {0, 0};
     RT_CUDA(cudaMemcpyAsync(cur, d_workspace, sizeof(cur), cudaMemcpyDeviceToHost, st));
     RT_CUDA(cudaStreamSynchronize(st));

@@ -77,8 +77,16 @@ def main():
     op = SLIMElastic(kwargs)
     cfg = op._config(X)
     tg = torch.arange(0, I, dtype=torch.int32, device="cuda")
+    D.set_option("solve_impl", 1)
+    ms1, sol1 = timeit(lambda: D.solve(G, I, tg, cfg), reps=2)
+    D.set_option("solve_impl", 2)
     ms, sol = timeit(lambda: D.solve(G, I, tg, cfg), reps=2)
+    res["solve_block_ms"] = ms1
     res["solve_ms"] = ms
+    res["solve_rows_equal"] = bool(torch.equal(sol1.rows, sol.rows))
+    res["solve_vals_maxdiff"] = float((sol1.vals - sol.vals).abs().max())
+    res["solve_cols_differ"] = int(((sol1.vals.view(-1, cfg.nn) != sol.vals.view(-1, cfg.nn)).any(dim=1)).sum()) if cfg.nn > 0 else None
+    res["solve_iters_differ"] = int((sol1.stats[:, 0] != sol.stats[:, 0]).sum())
     del G
     W = D.w_merge(None, I, sol)
     res["nnz_W"] = W.nnz
