@@ -227,7 +227,9 @@ int rt_rng_table(uint32_t seed, int64_t n, uint32_t *d_out, void *stream);
 
 /*
  * Solve the ElasticNet problems of `n_targets` target columns on the Gram matrix.
- *   d_G          [n_items, ldg] float32, complete for every item with a non-empty column
+ *   d_G          [n_items, ldg] float32, complete for every item with a non-empty column and symmetric
+ *                (rt_gram_finish / rt_gram_finish_p2p output is, bit for bit: the warp-per-column kernel
+ *                reads G[a][b] or G[b][a], whichever is convenient)
  *   d_targets    int32[n_targets] target item ids
  *   d_sel_in     optional int32[n_targets * nn]: candidate order to use instead of the built-in
  *                selection (score desc, ties -> larger item id first)

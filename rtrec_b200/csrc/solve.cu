@@ -649,13 +649,29 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
             }
         }
         __syncwarp();
-        // live x live Gram block (symmetric: load the lower triangle, store both halves)
-        for (int e = lane; e < m * m; e += 32) {
-            const int r = e / m, c = e - r * m;
-            if (c <= r) {
-                const float v = G[(size_t)S->feat[S->live[r]] * ld + S->feat[S->live[c]]];
-                Gs[r * m + c] = v;
-                Gs[c * m + r] = v;
+        // live x live Gram block (symmetric: load the lower triangle, store both halves).  The loads are random
+        // 4-byte reads of a matrix far larger than L2: four per lane are issued before any is consumed.
+        {
+            const int n_tri = m * (m + 1) / 2;
+            for (int e0 = lane; e0 < n_tri; e0 += 4 * 32) {
+                float v[4];
+                int rr[4], cc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = e0 + 32 * q;
+                    rr[q] = -1; cc[q] = 0; v[q] = 0.f;
+                    if (e < n_tri) {
+                        // e = r(r+1)/2 + c, c <= r
+                        int r = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                        while (r * (r + 1) / 2 > e) --r;
+                        while ((r + 1) * (r + 2) / 2 <= e) ++r;
+                        rr[q] = r; cc[q] = e - r * (r + 1) / 2;
+                        v[q] = __ldg(G + (size_t)S->feat[S->live[r]] * ld + S->feat[S->live[cc[q]]]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (rr[q] >= 0) { Gs[rr[q] * m + cc[q]] = v[q]; Gs[cc[q] * m + rr[q]] = v[q]; }
             }
         }
         __syncwarp();
@@ -687,10 +703,20 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
                     const int f = S->feat[k];
                     if (f == j) v = 0.0;
                     else {
+                        // row f of the symmetric G at the support columns: ns independent loads, four in flight
+                        const float *gf = G + (size_t)f * ld;
                         double hk = 0.0;
-                        for (int e = 0; e < ns; ++e) {
+                        int e = 0;
+                        for (; e + 3 < ns; e += 4) {
+                            const int s0 = S->list[e], s1 = S->list[e + 1], s2 = S->list[e + 2], s3 = S->list[e + 3];
+                            const float g0 = __ldg(gf + S->feat[S->live[s0]]), g1 = __ldg(gf + S->feat[S->live[s1]]);
+                            const float g2 = __ldg(gf + S->feat[S->live[s2]]), g3 = __ldg(gf + S->feat[S->live[s3]]);
+                            hk += (double)g0 * S->w[s0]; hk += (double)g1 * S->w[s1];
+                            hk += (double)g2 * S->w[s2]; hk += (double)g3 * S->w[s3];
+                        }
+                        for (; e < ns; ++e) {
                             const int sc = S->list[e];
-                            hk += (double)G[(size_t)S->feat[S->live[sc]] * ld + f] * S->w[sc];
+                            hk += (double)__ldg(gf + S->feat[S->live[sc]]) * S->w[sc];
                         }
                         v = (double)gj[f] - hk;
                     }
