@@ -347,25 +347,23 @@ __device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool
     if (tid == 0) { fs->cnt_gt = 0; fs->cnt_ge = 0; }
     __syncthreads();
     // ---- pass 1: bucket maxima (on floats) and eligible count ----------------------------------------
+    // 16-byte shared-memory loads when the array allows it (a thread's elements all fall into its one bucket,
+    // tid mod 128, whatever elements it visits)
     float m = -INFINITY;
     int ne = 0;
-    if (skip_zero) {
-#pragma unroll 8
-        for (int x = tid; x < N; x += NT) {
-            const float v = vals[x];
-            const bool ok = (v > -INFINITY) && (v != 0.0f);
-            m = ok ? fmaxf(m, v) : m;
-            ne += ok;
-        }
-    } else {
-#pragma unroll 8
-        for (int x = tid; x < N; x += NT) {
-            const float v = vals[x];
-            const bool ok = v > -INFINITY;
-            m = ok ? fmaxf(m, v) : m;
-            ne += ok;
-        }
+    const bool v4 = ((((uintptr_t)vals) & 15) == 0);
+    const int N4 = v4 ? (N >> 2) : 0;
+    auto see = [&](float v) {
+        const bool ok = skip_zero ? ((v > -INFINITY) && (v != 0.0f)) : (v > -INFINITY);
+        m = ok ? fmaxf(m, v) : m;
+        ne += ok;
+    };
+#pragma unroll 4
+    for (int q = tid; q < N4; q += NT) {
+        const float4 v = reinterpret_cast<const float4 *>(vals)[q];
+        see(v.x); see(v.y); see(v.z); see(v.w);
     }
+    for (int x = (N4 << 2) + tid; x < N; x += NT) see(vals[x]);
     if (ne) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], float_key(m));
     ne = warp_sum_i(ne);
     if (lane == 0) fs->wtot[0][warp] = ne;
@@ -389,11 +387,8 @@ __device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool
     // non-empty buckets than kk the kk-th maximum is 0 -> T = 1, below every eligible key)
     const float Tf = T > 1u ? fs_key_to_float(T) : -INFINITY;
     // ---- pass 2: collect everything >= T ---------------------------------------------------------------
-    for (int base = 0; base < N; base += NT) {
-        const int x = base + tid;
-        float v = -INFINITY;
-        if (x < N) v = vals[x];
-        bool take = (v >= Tf) && (v > -INFINITY);
+    auto consider = [&](int x, float v, bool valid) {
+        bool take = valid && (v >= Tf) && (v > -INFINITY);
         if (skip_zero) take = take && (v != 0.0f);
         const unsigned bal = __ballot_sync(0xffffffffu, take);
         if (bal) {
@@ -407,6 +402,23 @@ __device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
             const int pos = take ? basepos + __popc(bal & ((1u << lane) - 1u)) : FS_LIST;
             if (pos < FS_LIST) { fs->u.f.lkey[pos] = key; fs->u.f.lidx[pos] = x; }
+        }
+    };
+    {
+        const int N4r = ((N4 + NT - 1) / NT) * NT;   // whole-CTA iterations: the ballots need converged warps
+        for (int q = tid; q < N4r; q += NT) {
+            float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            const bool valid = q < N4;
+            if (valid) v = reinterpret_cast<const float4 *>(vals)[q];
+            const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+            if (__any_sync(0xffffffffu, valid && m4 >= Tf)) {
+                const int x0 = q << 2;
+                consider(x0, v.x, valid); consider(x0 + 1, v.y, valid); consider(x0 + 2, v.z, valid); consider(x0 + 3, v.w, valid);
+            }
+        }
+        for (int base = (N4 << 2); base < N; base += NT) {
+            const int x = base + tid;
+            consider(x, x < N ? vals[x] : -INFINITY, x < N);
         }
     }
     __syncthreads();

@@ -109,6 +109,7 @@ __global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of,
     n_chunks[jp] = (cptr[j + 1] - cptr[j] + G3_CHUNK - 1) / G3_CHUNK;
 }
 
+template <int SLICE>
 __global__ void __launch_bounds__(G3_WARPS * 32)
 gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_start, int R, int RW,
                   const int *__restrict__ orig_of, const int *__restrict__ cptr, const int *__restrict__ cidx,
@@ -117,7 +118,7 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                   unsigned long long *__restrict__ counter) {
     extern __shared__ __align__(16) float g3_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *slice = g3_smem + (size_t)warp * G3_SLICE;
+    float *slice = g3_smem + (size_t)warp * SLICE;
     const int n_rows = row_end - row_begin;
     const int R1 = R + 1;
     const unsigned long long n_tasks = (unsigned long long)(chunk_start[n_rows] - chunk_start[0]) * (unsigned)R1;
@@ -389,10 +390,14 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
     const int bs = 256;
     const int I = n_items;
     // ---- geometry --------------------------------------------------------------------------------
-    int R = (I + 8 * G3_SLICE - 1) / (8 * G3_SLICE);
+    // tuning switches (rt_set_option): "gram_slice" = floats per warp slice (1152 / 1728 / 2304),
+    // "gram_ranges" = number of shared-memory ranges R (0 = derive from the item count)
+    int RW = rt::option(rt::OPT_GRAM_SLICE);
+    if (RW != 1152 && RW != 2304) RW = G3_SLICE;
+    int R = rt::option(rt::OPT_GRAM_RANGES);
+    if (R <= 0) R = (I + 4 * RW - 1) / (4 * RW);   // head = a quarter of the catalogue, at most 4 ranges (measured: kbench)
     if (R < 1) R = 1;
     if (R > G3_MAX_R) R = G3_MAX_R;
-    const int RW = G3_SLICE;
     // ---- workspace -------------------------------------------------------------------------------
     Carver sizing(nullptr, (size_t)-1);
     auto plan = [&](Carver &c) {
@@ -469,15 +474,22 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
     // ---- lower triangle ----------------------------------------------------------------------------
     if (row_end > row_begin) {
         RT_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
-        const size_t smem = sizeof(float) * (size_t)G3_WARPS * G3_SLICE;
-        RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = sizeof(float) * (size_t)G3_WARPS * RW;
         int per_sm = (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         const int grid = rt::sm_count() * per_sm;
-        gram_lower_kernel<<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, d_orig_of,
-                                                            d_cptr, d_cidx, d_cval, P.cpos, P.hseg, P.pidx, P.pval, d_Gp,
-                                                            ldgp, P.counter);
+#define G3_LAUNCH(SL)                                                                                                   \
+        do {                                                                                                            \
+            RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gram_lower_kernel<SL><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
+                                                                    d_orig_of, d_cptr, d_cidx, d_cval, P.cpos, P.hseg,    \
+                                                                    P.pidx, P.pval, d_Gp, ldgp, P.counter);              \
+        } while (0)
+        if (RW == 1152) G3_LAUNCH(1152);
+        else if (RW == 2304) G3_LAUNCH(2304);
+        else G3_LAUNCH(G3_SLICE);
+#undef G3_LAUNCH
         RT_CHECK_LAUNCH();
     }
     return RT_OK;

@@ -100,7 +100,9 @@ __global__ void pack_count_kernel(const int *__restrict__ wrptr, const int *__re
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-    if (lane == 0) n_groups[w] = mine;
+    // rounded up to a multiple of 4 groups per warp of the scoring CTA: the scoring loop then needs no remainder
+    // handling (the extra groups are padding slots)
+    if (lane == 0) n_groups[w] = (mine + 4 * S3_NW - 1) / (4 * S3_NW) * (4 * S3_NW);
 }
 
 // one warp per (heavy row, tile): slot (position within bank, bank) <- (byte offset of the column in the score
@@ -243,22 +245,12 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
 #pragma unroll
                                     for (int r = 0; r < 8; ++r) S3_APPLY(e[r]);
                                 }
-                                if (gi + 3 * S3_NW < ge) {
+                                if (gi < ge) {   // group counts are multiples of 4 per warp (pack_count_kernel)
                                     int2 e[4];
 #pragma unroll
                                     for (int r = 0; r < 4; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32];
 #pragma unroll
                                     for (int r = 0; r < 4; ++r) S3_APPLY(e[r]);
-                                    gi += 4 * S3_NW;
-                                }
-                                {
-                                    // up to three groups left: loads first, then the updates
-                                    int2 e[3];
-#pragma unroll
-                                    for (int r = 0; r < 3; ++r)
-                                        e[r] = (gi + r * S3_NW < ge) ? base[(size_t)(gi + r * S3_NW) * 32] : make_int2((tile + lane) * 4, 0);
-#pragma unroll
-                                    for (int r = 0; r < 3; ++r) S3_APPLY(e[r]);
                                 }
 #undef S3_APPLY
                             } else {

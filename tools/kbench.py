@@ -52,14 +52,9 @@ def main():
     if "gram" in what:
         def g1():
             G.zero_(); D.gram(X, out=G); return None
-        ms1, _ = timeit(g1)
+        ms1, _ = timeit(g1, reps=1, warm=0)
         G1 = G.clone()
-        def g2():
-            G.zero_(); D.gram_cols(X, out=G); return None
-        ms2, _ = timeit(g2)
-        res["gram_v1_ms"] = ms1; res["gram_v2_ms"] = ms2
-        res["gram_equal"] = bool(torch.equal(G1, G))
-        res["gram_maxdiff"] = float((G1 - G).abs().max())
+        res["gram_v1_ms"] = ms1
         box = {}
         def g3a():
             box["L"] = D.gram_lower(X); return None
@@ -68,6 +63,12 @@ def main():
             D.gram_finish(box["L"], out=G); return None
         ms3b, _ = timeit(g3b)
         res["gram_v3_lower_ms"] = ms3a; res["gram_v3_finish_ms"] = ms3b
+        for sl, rg in ((1728, 3), (1728, 4), (1152, 3), (1152, 4), (2304, 2), (2304, 3)):
+            D.set_option("gram_slice", sl); D.set_option("gram_ranges", rg)
+            msv, _ = timeit(g3a)
+            D.gram_finish(box["L"], out=G)
+            res[f"gram_v3_lower_slice{sl}_r{rg}"] = {"ms": msv, "equal": bool(torch.equal(G1, G))}
+        D.set_option("gram_slice", 0); D.set_option("gram_ranges", 0)
         res["gram_v3_equal"] = bool(torch.equal(G1, G))
         res["gram_v3_maxdiff"] = float((G1 - G).abs().max())
         box.clear()
