@@ -62,43 +62,86 @@ def load_events(shape: str):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region.  NVML is initialised in this
+    process before the region starts and each sample is two cheap NVML calls; forking `nvidia-smi` inside the
+    region (the first version of this class) re-initialises NVML and enumerates every GPU per sample, which on an
+    8-GPU box with 8 ranks stalled CUDA calls for tens of milliseconds.  `nvidia-smi` remains the fallback when
+    the NVML binding is missing.  With several ranks only rank 0 samples (its own GPU)."""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
-        self.samples = []
+        self.enabled = enabled
+        self.samples = []          # (sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        self._handle = None
+        if enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the torch device
+                import torch
+                bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+                handle = None
+                if bus is not None:
+                    for k in range(pynvml.nvmlDeviceGetCount()):
+                        h = pynvml.nvmlDeviceGetHandleByIndex(k)
+                        if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                            handle = h
+                            break
+                self._handle = handle if handle is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+                self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+                self._nvml = pynvml
+            except Exception:
+                self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+        self.samples.append((sm, self._max, bool(r & n.nvmlClocksEventReasonHwSlowdown), bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                             bool(r & n.nvmlClocksEventReasonSwThermalSlowdown), bool(r & n.nvmlClocksEventReasonSwPowerCap)))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].replace(".", "").isdigit():
+            self.samples.append((float(parts[0]), float(parts[1]) if parts[1].replace(".", "").isdigit() else None,
+                                 *[p.lower().startswith("active") for p in parts[2:6]]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
-        self._thread.start()
+        if self.enabled:
+            self._thread.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._thread.join(timeout=6)
+        if self.enabled:
+            self._thread.join(timeout=6)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        sm = sorted(s[0] for s in self.samples)
+        mx = [s[1] for s in self.samples if s[1] is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.samples)}
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -230,7 +273,7 @@ def run_ours(args):
     barrier()
     # ---- timed: K steps, device-resident inputs
     _lib.load().rt_launch_count_reset()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         barrier()
         e0, e1 = ev_pair()
         t_wall0 = time.perf_counter()

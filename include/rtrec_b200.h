@@ -175,17 +175,21 @@ int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_
  * Multi-GPU form of rt_gram_finish: the slab exchange is fused with the mirror step over peer memory.
  * h_slabs[p] (HOST array of n_parts DEVICE pointers, p = part index) addresses the d_Gp buffer of rank p
  * as seen from this process: the own buffer for p == part, a CUDA IPC mapping (rt_ipc_open) of the
- * peer's buffer otherwise; all have the same ldgp.  Rows [h_cuts[p], h_cuts[p+1]) of the lower triangle
- * are read from slab p (NVLink P2P loads for p != part), stored into the own buffer and mirrored into
- * its upper triangle in one pass; with unpermute != 0 the symmetric matrix is then written in the
- * caller's item ids to d_G exactly like rt_gram_finish.  The caller orders the ranks: every rank must
- * have finished rt_gram_lower before any rank starts this call, and no rank may overwrite its slab
- * until every rank has finished it (two stream-ordered barriers, e.g. a one-element NCCL all-reduce).
+ * peer's buffer otherwise; all have the same ldgp.  The call is made three times per fit:
+ *   phase 0  tiles of this rank's stripe (and those touching its own slab) are read from the ranks that
+ *            computed them (NVLink P2P loads), stored into the own buffer and mirrored into its upper
+ *            triangle in one pass;
+ *   phase 1  the remaining tiles are read from their stripe rank, which holds them since phase 0 -- so
+ *            a large slab leaves its owner once, not once per peer, and every GPU sends about the same;
+ *   phase 2  the symmetric matrix is written in the caller's item ids to d_G exactly like rt_gram_finish.
+ * The caller orders the ranks with node barriers (e.g. a one-element NCCL all-reduce on the stream):
+ * every rank has finished rt_gram_lower before any phase 0, every phase 0 before any phase 1, and no
+ * rank overwrites its buffer until every rank has finished phase 1.
  */
 #define RT_MAX_PEERS 8
 int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part,
                        const int32_t *h_cuts, int64_t ldgp, const int32_t *d_rank_of,
-                       const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t unpermute, void *stream);
+                       const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t phase, void *stream);
 
 /*
  * Device buffers that other processes of the same node can map (CUDA IPC): rt_ipc_alloc returns a

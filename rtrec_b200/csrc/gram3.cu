@@ -283,10 +283,28 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_kernel(GramPeers P, floa
 
 // Same with 64 x 64 tiles and 16-byte accesses (needs ld % 4 == 0 and 16-byte aligned slabs): NVLink P2P
 // reads reach their bandwidth only with wide loads and many bytes in flight (4 x LDG.128 per thread).
-__global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, float *G, int n, int64_t ld) {
+//
+// Two phases keep every GPU's NVLink egress balanced although the slabs are not (slabs are balanced by
+// multiply-adds, and the slab of the unpopular tail holds ~45 % of the triangle's bytes at N = 8: if every
+// rank pulled it from its owner, that one GPU would have to send it seven times).  Every tile has a
+// "stripe" rank (a hash of its coordinates).  Phase 0: a rank processes the tiles of its own stripe and the
+// tiles touching its own slab, reading each row from its true owner -- the big slab leaves its owner only
+// once, spread over all peers.  Phase 1 (after a node barrier): every remaining tile is read from its stripe
+// rank, which has held it since phase 0.  Per-GPU egress: ~(N-1)/N of the triangle either way.
+__device__ __forceinline__ int gram_tile_stripe(int by, int bx, int n_parts) { return (by * 5 + bx * 3) % n_parts; }
+
+__global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, float *G, int n, int64_t ld, int phase) {
     __shared__ float tile[64][65];
     const int bx = blockIdx.x, by = blockIdx.y;
     if (bx > by) return;
+    const int stripe = gram_tile_stripe(by, bx, P.n_parts);
+    {
+        // does this tile belong to phase 0 on this rank?  (own stripe, or rows of the own slab inside the tile)
+        const int row_lo = by * 64, row_hi = min(by * 64 + 64, n);
+        const bool mine = row_lo < P.cuts[P.me + 1] && row_hi > P.cuts[P.me];
+        const bool first = (stripe == P.me) || mine;
+        if ((phase == 0) != first) return;
+    }
     const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;  // 16 threads cover the 64 columns of a row
     float4 v[4];
     int own[4];
@@ -300,16 +318,16 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, f
 #pragma unroll
             for (int p = 1; p < RT_MAX_PEERS; ++p) owner += (p < P.n_parts && row >= P.cuts[p]) ? 1 : 0;
             own[q] = owner;
-            v[q] = *reinterpret_cast<const float4 *>(P.src[owner] + (size_t)row * ld + col);
+            const int src = (phase == 0 || owner == P.me) ? owner : stripe;
+            v[q] = *reinterpret_cast<const float4 *>(P.src[src] + (size_t)row * ld + col);
         }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int r = r0 + 16 * q;
         const int row = by * 64 + r, col = bx * 64 + c4;
-        // entries right of the diagonal inside a float4 are not part of the lower triangle: keep the local value
-        // out of the tile (the transposed store below only uses entries with col < row) and store only the
-        // in-triangle prefix locally
+        // entries right of the diagonal inside a float4 are not part of the lower triangle: the transposed store
+        // below only uses entries with col < row, and only the in-triangle prefix is stored locally
         if (own[q] != P.me && row < n && col <= row) {
             float *dst = G + (size_t)row * ld + col;
             if (col + 3 <= row) *reinterpret_cast<float4 *>(dst) = v[q];
@@ -513,9 +531,10 @@ static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, co
 
 extern "C" int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part,
                                   const int32_t *h_cuts, int64_t ldgp, const int32_t *d_rank_of,
-                                  const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t unpermute, void *stream) {
+                                  const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t phase, void *stream) {
     RT_ARG(n_items > 0 && h_slabs && h_cuts && ldgp >= n_items, "arguments");
     RT_ARG(n_parts >= 1 && n_parts <= RT_MAX_PEERS && part >= 0 && part < n_parts, "part / n_parts");
+    RT_ARG(phase >= 0 && phase <= 2, "phase");
     for (int p = 0; p < n_parts; ++p) RT_ARG(h_slabs[p] != nullptr && h_cuts[p] <= h_cuts[p + 1], "slab pointers / cuts");
     RT_ARG(h_cuts[0] == 0 && h_cuts[n_parts] == n_items, "cuts must cover [0, n_items]");
     cudaStream_t st = (cudaStream_t)stream;
@@ -526,15 +545,19 @@ extern "C" int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, i
     float *local = (float *)h_slabs[part];
     bool wide = (ldgp % 4) == 0;
     for (int p = 0; p < n_parts; ++p) wide = wide && ((((uintptr_t)h_slabs[p]) & 15) == 0);
-    if (wide) {
-        const int nt = (n_items + 63) / 64;
-        gram_pull_mirror_v4_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
-    } else {
-        const int nt = (n_items + 31) / 32;
-        gram_pull_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+    if (phase <= 1) {
+        if (wide) {
+            const int nt = (n_items + 63) / 64;
+            gram_pull_mirror_v4_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp, phase);
+            RT_CHECK_LAUNCH();
+        } else if (phase == 0) {
+            // narrow fallback: one phase, every row straight from its owner
+            const int nt = (n_items + 31) / 32;
+            gram_pull_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(P, local, n_items, ldgp);
+            RT_CHECK_LAUNCH();
+        }
+        return RT_OK;
     }
-    RT_CHECK_LAUNCH();
-    if (!unpermute) return RT_OK;
     RT_ARG(d_rank_of && d_orig_of && d_G && ldg >= n_items && d_G != local, "unpermute arguments");
     return launch_unpermute(n_items, local, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
 }

@@ -221,27 +221,23 @@ def gram_lower(X: DeviceMatrix, part: int = 0, n_parts: int = 1, raw_ptr: Option
     return GramLower(Gp, rank_of, orig_of, list(cuts))
 
 
-def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: int, out=None):
-    """Fused slab exchange + mirror over peer memory, then the un-permuted symmetric G (rt_gram_finish_p2p).
-    ``slab_ptrs[p]``: address of rank p's slab buffer in this process (own buffer or IPC mapping)."""
+def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: int, out=None, barrier=None):
+    """Fused slab exchange + mirror over peer memory in two balanced phases, then the un-permuted symmetric G
+    (rt_gram_finish_p2p phases 0, 1, 2).  ``slab_ptrs[p]``: address of rank p's slab buffer in this process
+    (own buffer or IPC mapping).  ``barrier``: stream-ordered node barrier, called between the two pull
+    phases (omit when all slabs live in this process, as in the single-GPU test)."""
     t = require_cuda()
+    lib = _lib.load()
     n_parts = len(slab_ptrs)
     if out is None:
         out = t.empty((n_items, n_items), dtype=t.float32, device=dev())
     arr = (C.c_void_p * n_parts)(*[C.c_void_p(int(p)) for p in slab_ptrs])
     cuts = (C.c_int32 * (n_parts + 1))(*[int(c) for c in L.cuts])
-    check(_lib.load().rt_gram_finish_p2p(n_items, arr, n_parts, int(part), cuts, slab_ld(n_items), ptr(L.rank_of),
-                                         ptr(L.orig_of), ptr(out), n_items, 1, stream_ptr()), "rt_gram_finish_p2p")
-    return out
-
-
-def gram_finish(L: GramLower, out=None):
-    t = require_cuda()
-    I = L.Gp.shape[0]
-    if out is None:
-        out = t.empty((I, I), dtype=t.float32, device=dev())
-    check(_lib.load().rt_gram_finish(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, stream_ptr()),
-          "rt_gram_finish")
+    for phase in (0, 1, 2):
+        check(lib.rt_gram_finish_p2p(n_items, arr, n_parts, int(part), cuts, slab_ld(n_items), ptr(L.rank_of),
+                                     ptr(L.orig_of), ptr(out), n_items, phase, stream_ptr()), "rt_gram_finish_p2p")
+        if phase == 0 and barrier is not None:
+            barrier()
     return out
 
 

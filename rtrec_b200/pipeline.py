@@ -228,7 +228,7 @@ def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchan
         L = D.gram_lower(X, part=rank, n_parts=world, raw_ptr=slabs.own)
         mark("gram_lower")
         slabs.barrier()   # every slab is complete
-        G = D.gram_finish_p2p(L, slabs.ptrs, rank, X.n_items)
+        G = D.gram_finish_p2p(L, slabs.ptrs, rank, X.n_items, barrier=slabs.barrier)
         mark("gram_finish_p2p")
         return G
     L = D.gram_lower(X, part=rank, n_parts=world)

@@ -147,9 +147,18 @@ def test_gram_fused_pull_mirror_equals_single_pass():
             bufs.append(int(ptr_.value))
         parts = [D.gram_lower(dX, part=p, n_parts=n_parts, raw_ptr=bufs[p]) for p in range(n_parts)]
         assert all(q.cuts == parts[0].cuts for q in parts)
+        # the protocol of the real ranks, run in lock step: everybody phase 0, (barrier), everybody phase 1, then
+        # each rank un-permutes its own copy (phase 2)
+        t = D.torch()
+        arr = (C.c_void_p * n_parts)(*[C.c_void_p(b) for b in bufs])
+        cuts = (C.c_int32 * (n_parts + 1))(*parts[0].cuts)
+        outs = [t.empty((I, I), dtype=t.float32, device="cuda") for _ in range(n_parts)]
+        for phase in (0, 1, 2):
+            for me in range(n_parts):
+                _lib.check(lib.rt_gram_finish_p2p(I, arr, n_parts, me, cuts, D.slab_ld(I), D.ptr(parts[me].rank_of),
+                                                  D.ptr(parts[me].orig_of), D.ptr(outs[me]), I, phase, D.stream_ptr()))
         for me in range(n_parts):
-            G = D.gram_finish_p2p(parts[me], bufs, me, I).cpu().numpy()
-            assert np.array_equal(G, G_ref), f"rank {me}"  # pulls only write outside the puller's own slab
+            assert np.array_equal(outs[me].cpu().numpy(), G_ref), f"rank {me}"
     finally:
         D.torch().cuda.synchronize()
         for b in bufs:
