@@ -241,6 +241,16 @@ def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: 
     return out
 
 
+def gram_finish(L: GramLower, out=None):
+    t = require_cuda()
+    I = L.Gp.shape[0]
+    if out is None:
+        out = t.empty((I, I), dtype=t.float32, device=dev())
+    check(_lib.load().rt_gram_finish(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, stream_ptr()),
+          "rt_gram_finish")
+    return out
+
+
 def gram_full(X: DeviceMatrix, out=None):
     """Dense symmetric item-item Gram matrix G in item ids (K3, third generation)."""
     return gram_finish(gram_lower(X), out=out)

@@ -102,3 +102,28 @@ def test_metrics_known_answers():
     assert list(out) == ["precision", "recall", "f1", "ndcg", "hit_rate", "mrr", "map", "tp", "auc"]
     assert out["tp"] == 2
     assert M.compute_scores([], 3)["ndcg"] == 0.0
+
+
+def test_every_referenced_helper_exists():
+    """Every ``D.<name>`` / ``P.<name>`` the package, the bench, the tools and the tests refer to exists, and
+    every ``rt_*`` entry point called through ctypes has a prototype (a missing wrapper would otherwise only
+    show up on the GPU box)."""
+    import glob
+    import re
+    from rtrec_b200 import _lib, device as D, pipeline as P
+    files = (glob.glob(os.path.join(ROOT, "rtrec_b200", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "*.py"))
+             + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")])
+    missing = []
+    for f in files:
+        src = open(f).read()
+        for mod, obj, marker in (("D", D, "device as D"), ("P", P, "pipeline as P")):
+            if marker not in src:
+                continue
+            for name in set(re.findall(r"(?<![\w.])" + mod + r"\.([A-Za-z_]\w*)", src)):
+                if not hasattr(obj, name):
+                    missing.append((os.path.relpath(f, ROOT), f"{mod}.{name}"))
+        for a, b in set(re.findall(r"\blib\.(rt_\w+)|load\(\)\.(rt_\w+)", src)):
+            if (a or b) not in _lib.PROTOTYPES:
+                missing.append((os.path.relpath(f, ROOT), a or b))
+    assert not missing, missing
