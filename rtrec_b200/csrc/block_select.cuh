@@ -331,6 +331,27 @@ __device__ __forceinline__ float fs_key_to_float(uint32_t k) {
     return __uint_as_float(u);
 }
 
+// (nth+1)-th largest of the 128 bucket maxima, multiplicity counted, by warp 0: every lane holds four maxima and
+// each round removes one instance of the current maximum (REDUX.MAX + ballot).  `nth` rounds of ~12 instructions
+// instead of the 128 x 128 compare matrix (5 % of the scoring kernel's instructions, profiles/r1z_*).  The result
+// (0 when fewer than nth+1 buckets are non-empty) is left in fs->T; the caller synchronises.
+__device__ __forceinline__ void fs_nth_bucket_max(FastSelScratch *fs, int nth) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    uint32_t k0 = fs->u.f.bmax[lane], k1 = fs->u.f.bmax[lane + 32], k2 = fs->u.f.bmax[lane + 64], k3 = fs->u.f.bmax[lane + 96];
+    uint32_t M = 0u;
+    for (int r = 0; r <= nth; ++r) {
+        const uint32_t lm = max(max(k0, k1), max(k2, k3));
+        M = __reduce_max_sync(0xffffffffu, lm);
+        if (M == 0u) break;
+        const unsigned has = __ballot_sync(0xffffffffu, lm == M);
+        if (lane == __ffs(has) - 1) {
+            if (k0 == M) k0 = 0u; else if (k1 == M) k1 = 0u; else if (k2 == M) k2 = 0u; else k3 = 0u;
+        }
+    }
+    if (lane == 0) fs->T = M;
+}
+
 __device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool skip_zero, FastSelScratch *fs, int *out_idx,
                                     uint32_t *out_key) {
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = (NT + 31) >> 5;
@@ -346,45 +367,64 @@ __device__ inline int block_top_n_fast_f32(const float *vals, int N, int n, bool
     if (tid < FS_BUCKETS) fs->u.f.bmax[tid] = 0u;
     if (tid == 0) { fs->cnt_gt = 0; fs->cnt_ge = 0; }
     __syncthreads();
-    // ---- pass 1: bucket maxima (on floats) and eligible count ----------------------------------------
     // 16-byte shared-memory loads when the array allows it (a thread's elements all fall into its one bucket,
     // tid mod 128, whatever elements it visits)
-    float m = -INFINITY;
-    int ne = 0;
     const bool v4 = ((((uintptr_t)vals) & 15) == 0);
     const int N4 = v4 ? (N >> 2) : 0;
-    auto see = [&](float v) {
-        const bool ok = skip_zero ? ((v > -INFINITY) && (v != 0.0f)) : (v > -INFINITY);
-        m = ok ? fmaxf(m, v) : m;
-        ne += ok;
-    };
+    // ---- pass 1, common case: RAW bucket maxima, one FMNMX per element ----------------------------------
+    // (the eligibility tests and the eligible count were 11 instructions per element = 15 % of the scoring
+    // kernel, profiles/r1z_*).  The n-th largest raw maximum T is the threshold the exact pass would find
+    // whenever it is itself eligible-and-decisive: dense mode -> T > -inf (n non-empty buckets, so n eligible
+    // elements exist); sparse mode -> T > 0 (the n leading buckets have positive maxima, which are eligible, and a
+    // bucket whose raw maximum is 0 has no eligible element above T).  Otherwise the exact pass below runs.
+    {
+        float m = -INFINITY;
 #pragma unroll 4
-    for (int q = tid; q < N4; q += NT) {
-        const float4 v = reinterpret_cast<const float4 *>(vals)[q];
-        see(v.x); see(v.y); see(v.z); see(v.w);
-    }
-    for (int x = (N4 << 2) + tid; x < N; x += NT) see(vals[x]);
-    if (ne) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], float_key(m));
-    ne = warp_sum_i(ne);
-    if (lane == 0) fs->wtot[0][warp] = ne;
-    __syncthreads();
-    int n_elig = 0;
-    for (int w = 0; w < nwarps; ++w) n_elig += fs->wtot[0][w];
-    const int kk = min(n, n_elig);
-    if (kk == 0) return 0;
-    if (tid < FS_BUCKETS) {
-        const uint32_t bm = fs->u.f.bmax[tid];
-        int rank = 0;
-        for (int f = 0; f < FS_BUCKETS; ++f) {
-            const uint32_t kf = fs->u.f.bmax[f];
-            rank += (kf > bm) || (kf == bm && f < tid);
+        for (int q = tid; q < N4; q += NT) {
+            const float4 v = reinterpret_cast<const float4 *>(vals)[q];
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
         }
-        if (rank == kk - 1) fs->T = bm == 0u ? 1u : bm;
+        for (int x = (N4 << 2) + tid; x < N; x += NT) m = fmaxf(m, vals[x]);
+        if (m > -INFINITY) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], float_key(m));
     }
     __syncthreads();
-    const uint32_t T = fs->T;
-    // T is the key of an eligible element here (kk <= number of non-empty buckets is not guaranteed: with fewer
-    // non-empty buckets than kk the kk-th maximum is 0 -> T = 1, below every eligible key)
+    fs_nth_bucket_max(fs, n - 1);
+    __syncthreads();
+    uint32_t T = fs->T;
+    int kk = n;
+    const bool raw_ok = skip_zero ? (T > 0x80000000u) : (T != 0u);   // float_key(0.0f) == 0x80000000
+    if (!raw_ok) {
+        // ---- pass 1, exact: bucket maxima over eligible elements and the eligible count ------------------
+        __syncthreads();
+        if (tid < FS_BUCKETS) fs->u.f.bmax[tid] = 0u;
+        __syncthreads();
+        float m = -INFINITY;
+        int ne = 0;
+        auto see = [&](float v) {
+            const bool ok = skip_zero ? ((v > -INFINITY) && (v != 0.0f)) : (v > -INFINITY);
+            m = ok ? fmaxf(m, v) : m;
+            ne += ok;
+        };
+        for (int q = tid; q < N4; q += NT) {
+            const float4 v = reinterpret_cast<const float4 *>(vals)[q];
+            see(v.x); see(v.y); see(v.z); see(v.w);
+        }
+        for (int x = (N4 << 2) + tid; x < N; x += NT) see(vals[x]);
+        if (ne) atomicMax(&fs->u.f.bmax[tid & (FS_BUCKETS - 1)], float_key(m));
+        ne = warp_sum_i(ne);
+        if (lane == 0) fs->wtot[0][warp] = ne;
+        __syncthreads();
+        int n_elig = 0;
+        for (int w = 0; w < nwarps; ++w) n_elig += fs->wtot[0][w];
+        kk = min(n, n_elig);
+        if (kk == 0) return 0;
+        fs_nth_bucket_max(fs, kk - 1);
+        __syncthreads();
+        T = fs->T;
+        if (T == 0u) T = 1u;   // fewer non-empty buckets than kk: below every eligible key
+    }
+    // T is the key of an eligible element here, or 1 (kk <= number of non-empty buckets is not guaranteed: with
+    // fewer non-empty buckets than kk the kk-th maximum is 0 -> T = 1, below every eligible key)
     const float Tf = T > 1u ? fs_key_to_float(T) : -INFINITY;
     // ---- pass 2: collect everything >= T ---------------------------------------------------------------
     auto consider = [&](int x, float v, bool valid) {

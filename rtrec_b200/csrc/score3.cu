@@ -100,9 +100,9 @@ __global__ void pack_count_kernel(const int *__restrict__ wrptr, const int *__re
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-    // rounded up to a multiple of 4 groups per warp of the scoring CTA: the scoring loop then needs no remainder
-    // handling (the extra groups are padding slots)
-    if (lane == 0) n_groups[w] = (mine + 4 * S3_NW - 1) / (4 * S3_NW) * (4 * S3_NW);
+    // rounded up to one group per warp of the scoring CTA: every warp then runs the same number of batches (the
+    // extra groups are padding slots)
+    if (lane == 0) n_groups[w] = (mine + S3_NW - 1) / S3_NW * S3_NW;
 }
 
 // one warp per (heavy row, tile): slot (position within bank, bank) <- (byte offset of the column in the score
@@ -172,7 +172,11 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
             const int t1 = min(t0 + tile, j_end);
             const int width = t1 - t0;
             const bool whole = (t0 == 0 && t1 == n_items);
-            for (int x = tid; x < width; x += S3_NT) acc[x] = 0.0f;
+            {   // tile starts are 16-byte aligned (tile is a multiple of 32 floats)
+                const int w4 = width >> 2;
+                for (int x = tid; x < w4; x += S3_NT) reinterpret_cast<float4 *>(acc)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int x = (w4 << 2) + tid; x < width; x += S3_NT) acc[x] = 0.0f;
+            }
             // ---------------- accumulate: chunks of the user's row ----------------
             for (int c0 = r0; c0 < r1; c0 += S3_CH) {
                 __syncthreads();  // previous chunk fully applied (and acc zeroed) before st.* is rewritten
@@ -213,54 +217,71 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                     __syncthreads();
                 }
                 const int n = sh.n_rows;
-                for (int g = 0; g < n; g += S3_GROUP) {
-                    int hj[S3_GROUP];
-                    float hv[S3_GROUP];
-                    // heads of up to 8 light rows: all loads are independent and issued back to back
-#pragma unroll
-                    for (int s = 0; s < S3_GROUP; ++s) {
-                        hj[s] = -1; hv[s] = 0.f;
-                        if (g + s < n) {
-                            const int b = sh.u.st.b[g + s];
-                            const int e = sh.u.st.a[g + s] + tid;
-                            if (b >= 0 && e < b) { hj[s] = wridx[e]; hv[s] = wrval[e]; }
+                int s = 0;
+                while (s < n) {   // every branch below is uniform across the CTA (the staged list is shared)
+                    if (sh.u.st.b[s] < 0) {
+                        // ---- heavy row: warp w takes groups a+w, a+w+16, ... (every warp the same number: group counts
+                        // are multiples of 16, pack_count_kernel), eight loads in flight, then 4 / 2 / 1 for the rest.
+                        // All tile reads of a batch are issued before its first write: the slots of one lane within a
+                        // row are distinct columns (or the lane's own dummy float, which only ever receives + x*0), so
+                        // a batch carries no dependency; it is written read-all / add / write-all because the compiler
+                        // must otherwise assume aliasing and chains LDS -> FADD -> STS per entry (the short-scoreboard
+                        // stall of profiles/r1z_*: 16.5 -> 14.2 ms).  Prefetching the next row's first batch across
+                        // the row barrier was measured as well (profiles/r2a_*: 14.35 ms) and dropped.
+                        {
+                            const int2 *base = ell + lane;
+                            char *accb = (char *)acc;
+                            const float x = sh.u.st.x[s];
+                            const int ge = ~sh.u.st.b[s];
+                            int gi = sh.u.st.a[s] + warp;
+#define S3_BATCH(NB)                                                                                       \
+                            {                                                                              \
+                                int2 e[NB];                                                                \
+                                float v[NB];                                                               \
+                                _Pragma("unroll") for (int r = 0; r < NB; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32]; \
+                                _Pragma("unroll") for (int r = 0; r < NB; ++r) v[r] = *(const float *)(accb + e[r].x);     \
+                                _Pragma("unroll") for (int r = 0; r < NB; ++r) v[r] = __fadd_rn(v[r], __fmul_rn(x, __int_as_float(e[r].y))); \
+                                _Pragma("unroll") for (int r = 0; r < NB; ++r) *(float *)(accb + e[r].x) = v[r];           \
+                            }
+                            for (; gi + 7 * S3_NW < ge; gi += 8 * S3_NW) S3_BATCH(8)
+                            if (gi + 3 * S3_NW < ge) { S3_BATCH(4) gi += 4 * S3_NW; }
+                            if (gi + S3_NW < ge) { S3_BATCH(2) gi += 2 * S3_NW; }
+                            if (gi < ge) S3_BATCH(1)
+#undef S3_BATCH
+                            __syncthreads();
+                            ++s;
                         }
-                    }
+                    } else {
+                        // ---- up to 8 consecutive light rows: the heads (first 512 entries) are fetched together, all
+                        // loads independent and issued back to back, then applied row by row
+                        int hj[S3_GROUP];
+                        float hv[S3_GROUP];
+                        int cnt = 0;
 #pragma unroll
-                    for (int s = 0; s < S3_GROUP; ++s) {
-                        if (g + s < n) {   // uniform across the CTA
-                            const float x = sh.u.st.x[g + s];
-                            const int b = sh.u.st.b[g + s];
-                            if (b < 0) {
-                                // heavy row: warp w takes groups a+w, a+w+16, ...; four loads in flight
-                                const int ge = ~b;
-                                const int2 *base = ell + lane;
-                                char *accb = (char *)acc;
-                                int gi = sh.u.st.a[g + s] + warp;
-#define S3_APPLY(E) { float *d = (float *)(accb + (E).x); *d = __fadd_rn(*d, __fmul_rn(x, __int_as_float((E).y))); }
-                                for (; gi + 7 * S3_NW < ge; gi += 8 * S3_NW) {
-                                    int2 e[8];
-#pragma unroll
-                                    for (int r = 0; r < 8; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32];
-#pragma unroll
-                                    for (int r = 0; r < 8; ++r) S3_APPLY(e[r]);
-                                }
-                                if (gi < ge) {   // group counts are multiples of 4 per warp (pack_count_kernel)
-                                    int2 e[4];
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) e[r] = base[(size_t)(gi + r * S3_NW) * 32];
-#pragma unroll
-                                    for (int r = 0; r < 4; ++r) S3_APPLY(e[r]);
-                                }
-#undef S3_APPLY
-                            } else {
-                                if (hj[s] >= 0) { float *d = &acc[hj[s] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, hv[s])); }
-                                for (int e = sh.u.st.a[g + s] + tid + S3_NT; e < b; e += S3_NT) {
-                                    float *d = &acc[wridx[e] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, wrval[e]));
+                        for (int t = 0; t < S3_GROUP; ++t) {
+                            hj[t] = -1; hv[t] = 0.f;
+                            if (cnt == t && s + t < n) {
+                                const int b = sh.u.st.b[s + t];
+                                if (b >= 0) {
+                                    ++cnt;
+                                    const int e = sh.u.st.a[s + t] + tid;
+                                    if (e < b) { hj[t] = wridx[e]; hv[t] = wrval[e]; }
                                 }
                             }
-                            __syncthreads();
                         }
+#pragma unroll
+                        for (int t = 0; t < S3_GROUP; ++t) {
+                            if (t < cnt) {
+                                const float x = sh.u.st.x[s + t];
+                                const int b = sh.u.st.b[s + t];
+                                if (hj[t] >= 0) { float *d = &acc[hj[t] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, hv[t])); }
+                                for (int e = sh.u.st.a[s + t] + tid + S3_NT; e < b; e += S3_NT) {
+                                    float *d = &acc[wridx[e] - t0]; *d = __fadd_rn(*d, __fmul_rn(x, wrval[e]));
+                                }
+                                __syncthreads();
+                            }
+                        }
+                        s += cnt;
                     }
                 }
             }
@@ -451,10 +472,9 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
         S3_CUB(cub::DeviceRadixSort::SortPairsDescending(d_tmp__, tmp_bytes__, keys, keys2, idx, idx2, n_query, 0, 32, st));
         d_order = idx2;
     }
-    recommend3_kernel<<<grid, S3_NT, smem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval,
-                                                d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles, n_items, j_begin, j_end,
-                                                k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next,
-                                                d_order);
+    recommend3_kernel<<<grid, S3_NT, smem, st>>>(
+        d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles,
+        n_items, j_begin, j_end, k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next, d_order);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -100,7 +100,7 @@ def main():
             ms2, o2 = timeit(lambda: D.recommend(X, users, W, 10, True, mode))
             res[f"score_{name}_v1_ms"] = ms1; res[f"score_{name}_v2_ms"] = ms2
             D.set_option("score_impl", 3)
-            for min_row in (512, 768, 1536, 3072):
+            for min_row in (768, 1536):
                 D.PACK_MIN_ROW = min_row
                 W.packs = None
                 ms3, o3 = timeit(lambda: D.recommend(X, users, W, 10, True, mode))
