@@ -15,8 +15,9 @@ solves (K4) -> W assembly (K5) -> fused scoring/filter/top-10 for every user (K6
 * ``cpu_baseline`` / ``--impl reference``: the CPU port of the reference path (oracle/, all host
   threads) on a bounded sample of the same workload, extrapolated to the full shape.
 
-N > 1 (torchrun): item columns are sharded across ranks (strong scaling on the fixed shape);
-Gram rows are exchanged with NCCL broadcasts, per-rank top-10 lists with an all-gather.
+N > 1 (torchrun): item columns are sharded across ranks (strong scaling on the fixed shape); every rank
+completes the Gram rows of its own targets out of peer memory (NVLink), the solver outputs (a few MB) and
+the per-rank top-10 lists are all-gathered with NCCL.
 """
 import argparse
 import json
@@ -238,14 +239,19 @@ def run_ours(args):
         cfg = op._config(X)
         t = torch
         j0, j1 = P.item_shard(X.n_items, rank, world)
-        G = P.gram_sharded(X, rank=rank, world=world, exchange=args.exchange, marks=mark)
-        if world > 1 and args.scoring == "query":
-            tg = P.item_stride(X.n_items, rank, world)   # interleaved targets: balanced whatever the id order
-        else:
-            tg = t.arange(j0, j1, dtype=t.int32, device="cuda")
-        res = D.solve(G, X.n_items, tg, cfg)
-        mark("solve")
-        del G
+        res = None
+        if world > 1 and args.exchange == "rows" and args.scoring == "query":
+            # owner-rows fit: no full Gram exchange (None = CUDA IPC unavailable on this node, agreed by all ranks)
+            res = P.fit_owner_rows(X, cfg, rank=rank, world=world, marks=mark)
+        if res is None:
+            G = P.gram_sharded(X, rank=rank, world=world, exchange="nccl" if args.exchange == "nccl" else "p2p", marks=mark)
+            if world > 1 and args.scoring == "query":
+                tg = P.item_stride(X.n_items, rank, world)   # interleaved targets: balanced whatever the id order
+            else:
+                tg = t.arange(j0, j1, dtype=t.int32, device="cuda")
+            res = D.solve(G, X.n_items, tg, cfg)
+            mark("solve")
+            del G
         if world > 1 and args.scoring == "query":
             res = P.gather_solve_results(res, world)
             mark("w_allgather")
@@ -323,7 +329,8 @@ def run_ours(args):
     nn = kwargs.get("nn_feature_selection") or X.n_items
     m_live = stats[:, 3]
     solve_bytes = float((4.0 * X.n_items + 4.0 * (m_live * m_live + m_live) + e_bytes * nn).sum())
-    gram_ms = phase_ms.get("gram_lower", 0.0) + phase_ms.get("gram_finish", 0.0) + phase_ms.get("gram_finish_p2p", 0.0)
+    gram_ms = (phase_ms.get("gram_lower", 0.0) + phase_ms.get("gram_finish", 0.0) + phase_ms.get("gram_finish_p2p", 0.0)
+               + phase_ms.get("gram_rows", 0.0) + phase_ms.get("gram_exchange", 0.0))
     kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0), solve_bytes), "recommend": (rec_ms, rec_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9
@@ -426,8 +433,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml20m", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: Gram slab exchange fused with the mirror kernel over peer memory (default) or NCCL broadcasts")
+    ap.add_argument("--exchange", default="rows", choices=["rows", "p2p", "nccl"],
+                    help="N>1: 'rows' = every rank completes only the Gram rows of its own targets from peer memory and the "
+                         "solver gathers foreign entries over NVLink (default); 'p2p' = whole-triangle exchange fused with the "
+                         "mirror kernel over peer memory; 'nccl' = whole-triangle exchange with NCCL broadcasts")
     ap.add_argument("--scoring", default="query", choices=["query", "item"],
                     help="N>1: partition scoring by query users (W all-gathered, default) or by item columns (top-k merge)")
     args = ap.parse_args()

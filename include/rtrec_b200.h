@@ -192,6 +192,40 @@ int rt_gram_finish_p2p(int32_t n_items, const void *const *h_slabs, int32_t n_pa
                        const int32_t *d_orig_of, float *d_G, int64_t ldg, int32_t phase, void *stream);
 
 /*
+ * Multi-GPU fit without a full Gram exchange ("owner rows").  Replaces, like rt_gram_lower, the per-column
+ * `X.T.dot(y)` of slim_elastic.py:141 -- for the target columns a GPU owns -- and hands the solver rows that may
+ * live on a peer GPU.
+ *
+ * Ownership is block-cyclic in popularity-rank space: the 64-row block b of the rank-space Gram matrix belongs
+ * to part b % n_parts and is stored at local block b / n_parts of that part's buffers (rt_gram_block_rows gives
+ * the buffer height `rows_alloc`, identical on every part, and the number of real rows `rows_own`).  Per fit:
+ *   1. rt_gram_lower_blocks   lower-triangle part (columns <= row) of the own rows into d_slab
+ *                             [rows_alloc, ldgp] (zero-filled by the caller); also writes rank_of / orig_of;
+ *   2. node barrier, then rt_gram_pull_cols: the rest of every own row is the transposed column below it in
+ *                             the triangle; its 64 x 64 tiles are read out of the owners' slabs (h_slabs[p]: own
+ *                             buffer or CUDA IPC mapping, NVLink P2P loads) and stored transposed.  Each GPU
+ *                             pulls (N-1)/N^2 of the matrix; egress is balanced by construction;
+ *   3. rt_gram_unpermute_rows columns back to item ids: d_rows[r][i] = d_slab[r][rank_of[i]] (rows keep
+ *                             their local position), into a second peer-mapped buffer;
+ *   4. rt_gram_row_slots      d_slots[i] = (owner part << 24) | local row of item i;
+ *   5. node barrier, then rt_slim_solve_rows on the own targets (the items of the own blocks): rows of other
+ *                             targets' candidates are gathered from the peers' d_rows through h_bases.
+ * No rank may overwrite its buffers before every rank has finished step 5 (node barrier at the start of
+ * the next fit).  With n_parts = 1 the result equals rt_gram_lower + rt_gram_finish + rt_slim_solve bit for
+ * bit; with n_parts > 1 every row is assembled from the same lower-triangle values, so W is identical too.
+ */
+int rt_gram_block_rows(int32_t n_items, int32_t n_parts, int32_t part, int32_t *h_rows_alloc, int32_t *h_rows_own);
+int rt_gram_lower_blocks(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                         const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                         int64_t nnz, int32_t part, int32_t n_parts, float *d_slab, int64_t ldgp,
+                         int32_t *d_rank_of, int32_t *d_orig_of, void *stream);
+int rt_gram_pull_cols(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part, int64_t ldgp,
+                      void *stream);
+int rt_gram_unpermute_rows(int32_t n_rows, int32_t n_items, const float *d_slab, int64_t ldgp,
+                           const int32_t *d_rank_of, float *d_rows, int64_t ldg, void *stream);
+int rt_gram_row_slots(int32_t n_items, const int32_t *d_rank_of, int32_t n_parts, int32_t *d_slots, void *stream);
+
+/*
  * Device buffers that other processes of the same node can map (CUDA IPC): rt_ipc_alloc returns a
  * cudaMalloc'ed pointer and its 64-byte handle; a peer process passes the handle to rt_ipc_open and
  * gets a pointer valid in its own address space (peer access over NVLink is enabled on demand).
@@ -254,6 +288,16 @@ int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, const int32_t 
                   const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
                   int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
                   int64_t *h_needed, int32_t *d_stats, void *stream);
+
+/* rt_slim_solve on the owner-rows layout (see rt_gram_lower_blocks): row i of G is read from buffer
+ * h_bases[d_rowslot[i] >> 24] (HOST array of n_bases DEVICE pointers: own memory or CUDA IPC mappings of the
+ * peers' row buffers, 16-byte aligned, common leading dimension ldg, a multiple of 4) at local row
+ * d_rowslot[i] & 0xffffff.  Every other argument as rt_slim_solve. */
+int rt_slim_solve_rows(const void *const *h_bases, int32_t n_bases, const int32_t *d_rowslot, int64_t ldg,
+                       int32_t n_items, const int32_t *d_targets, int32_t n_targets, const rt_fit_config *cfg,
+                       const int32_t *d_sel_in, const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out,
+                       int64_t *d_out_off, int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals,
+                       int64_t out_cap, int64_t *h_needed, int32_t *d_stats, void *stream);
 
 /*
  * Assemble / merge the item-similarity matrix W (CSC, n_items x n_items) from solver output,

@@ -63,6 +63,11 @@ PROTOTYPES = {
     "rt_gram": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
     "rt_gram_lower": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, C.POINTER(_I32), _P]),
     "rt_gram_finish": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P]),
+    "rt_gram_block_rows": (C.c_int, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
+    "rt_gram_lower_blocks": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
+    "rt_gram_pull_cols": (C.c_int, [_I32, _P, _I32, _I32, _I64, _P]),
+    "rt_gram_unpermute_rows": (C.c_int, [_I32, _I32, _P, _I64, _P, _P, _I64, _P]),
+    "rt_gram_row_slots": (C.c_int, [_I32, _P, _I32, _P, _P]),
     "rt_gram_finish_p2p": (C.c_int, [_I32, _P, _I32, _I32, C.POINTER(_I32), _I64, _P, _P, _P, _I64, _I32, _P]),
     "rt_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P), _P]),
     "rt_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
@@ -71,6 +76,8 @@ PROTOTYPES = {
     "rt_memset": (C.c_int, [_P, _I32, C.c_size_t, _P]),
     "rt_csr_split": (C.c_int, [_I32, _P, _P, _I32, _I32, _I32, _P, _P]),
     "rt_rng_table": (C.c_int, [_U32, _I64, _P, _P]),
+    "rt_slim_solve_rows": (C.c_int, [_P, _I32, _P, _I64, _I32, _P, _I32, C.POINTER(FitConfig), _P, _P, _I64, _P, _P, _P, _P, _P,
+                                     _I64, C.POINTER(_I64), _P, _P]),
     "rt_slim_solve": (C.c_int, [_P, _I64, _I32, _P, _I32, C.POINTER(FitConfig), _P, _P, _I64, _P, _P, _P, _P, _P, _I64,
                                 C.POINTER(_I64), _P, _P]),
     "rt_w_merge": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, C.POINTER(_I64), _P]),

@@ -28,6 +28,7 @@
 // the symmetric formulation reads half of S_j.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -101,13 +102,19 @@ __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict
     }
 }
 
+// blk_parts > 0: block-cyclic ownership (64-row block b of the rank-space matrix belongs to part b % blk_parts);
+// rows of other parts get no chunks, so the task list of the lower-triangle kernel only holds own rows
 __global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of, const int *__restrict__ cptr,
-                                   int *__restrict__ n_chunks) {
+                                   int *__restrict__ n_chunks, int blk_parts, int blk_me) {
     const int jp = blockIdx.x * blockDim.x + threadIdx.x;
     if (jp >= n_items) return;
     const int j = orig_of[jp];
-    n_chunks[jp] = (cptr[j + 1] - cptr[j] + G3_CHUNK - 1) / G3_CHUNK;
+    const bool mine = blk_parts <= 0 || ((jp >> 6) % blk_parts) == blk_me;
+    n_chunks[jp] = mine ? (cptr[j + 1] - cptr[j] + G3_CHUNK - 1) / G3_CHUNK : 0;
 }
+
+// local row of rank-space row jp in the slab of its owner under block-cyclic ownership
+__host__ __device__ __forceinline__ int blk_local_row(int jp, int blk_parts) { return (((jp >> 6) / blk_parts) << 6) | (jp & 63); }
 
 template <int SLICE>
 __global__ void __launch_bounds__(G3_WARPS * 32)
@@ -115,7 +122,7 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                   const int *__restrict__ orig_of, const int *__restrict__ cptr, const int *__restrict__ cidx,
                   const float *__restrict__ cval, const int *__restrict__ cpos, const int *__restrict__ hseg,
                   const int *__restrict__ pidx, const float *__restrict__ pval, float *__restrict__ Gp, int64_t ld,
-                  unsigned long long *__restrict__ counter) {
+                  unsigned long long *__restrict__ counter, int blk_parts) {
     extern __shared__ __align__(16) float g3_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *slice = g3_smem + (size_t)warp * SLICE;
@@ -139,7 +146,8 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
         const int c0 = cptr[j], c1 = cptr[j + 1];
         const int e0 = c0 + (cc - chunk_start[lo_r]) * G3_CHUNK;
         const int e1 = min(e0 + G3_CHUNK, c1);
-        float *g_row = Gp + (size_t)jp * ld;
+        // block-cyclic mode: the slab only holds the rows of this part, densely packed
+        float *g_row = Gp + (size_t)(blk_parts > 0 ? blk_local_row(jp, blk_parts) : jp) * ld;
         if (g < R) {
             const int lo = g * RW;
             const int width = min(RW, jp + 1 - lo);
@@ -358,14 +366,16 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, f
 }
 
 // G[orig_of[jp]][x] = G'[jp][rank_of[x]]: one CTA per row; the row is staged in shared memory when it fits
-__global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n,
+// (orig_of == nullptr: rows keep their position -- the owner-rows layout of the multi-GPU fit, where only the columns go
+// back to item ids and rows are addressed through rt_gram_row_slots)
+__global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n_rows, int n,
                                                               const int *__restrict__ rank_of, const int *__restrict__ orig_of,
                                                               float *__restrict__ G, int64_t ld, int stage) {
     extern __shared__ __align__(16) float row_s[];
     const int NT = blockDim.x;
-    for (int jp = blockIdx.x; jp < n; jp += gridDim.x) {
+    for (int jp = blockIdx.x; jp < n_rows; jp += gridDim.x) {
         const float *src = Gp + (size_t)jp * ldp;
-        float *dst = G + (size_t)orig_of[jp] * ld;
+        float *dst = G + (size_t)(orig_of ? orig_of[jp] : jp) * ld;
         if (stage) {
             __syncthreads();
 #pragma unroll 4
@@ -378,6 +388,70 @@ __global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__res
             for (int x = threadIdx.x; x < n; x += NT) dst[x] = src[rank_of[x]];
         }
     }
+}
+
+// ---- multi-GPU, owner-rows layout -------------------------------------------------------------------------------
+// Block-cyclic ownership: 64-row block b of the rank-space matrix belongs to part b % n_parts and sits at local block
+// b / n_parts of that part's slab.  After rt_gram_lower_blocks a slab holds the lower-triangle part of its rows (columns
+// <= row).  The rest of a row is the transposed column of the triangle below it, spread over every part: this kernel
+// reads those 64 x 64 tiles straight out of their owners' slabs (CUDA IPC mappings, NVLink P2P loads for peers) and
+// stores them transposed into the local rows.  A part only ever pulls the columns of ITS rows: (N-1)/N^2 of the matrix
+// per GPU instead of the whole triangle, egress and ingress balanced by construction, one phase.  Writers touch
+// columns > row of their own rows, readers columns <= row: no element is read and written in the same pass.
+struct GramRowPeers {
+    const float *src[RT_MAX_PEERS];
+    int n_parts;
+    int me;
+};
+
+__global__ void __launch_bounds__(256) gram_pull_cols_kernel(GramRowPeers P, float *local, int n, int64_t ld) {
+    __shared__ float tile[64][65];
+    const int bx = blockIdx.x;                  // source row block (global index) = destination column block
+    const int lb = blockIdx.y;                  // local block of the destination rows
+    const int bq = lb * P.n_parts + P.me;       // its global index
+    if (bx < bq || bq * 64 >= n) return;
+    const float *src = P.src[bx % P.n_parts] + (size_t)(bx / P.n_parts) * 64 * ld;
+    const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;  // 16 threads cover the 64 columns of a row
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + 16 * q;
+        const int row = bx * 64 + r, col = bq * 64 + c4;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // col <= row: the float4 starts inside the triangle (on the diagonal tile it may run past the diagonal; those
+        // entries are never used by the transposed store below)
+        if (row < n && col <= row) v[q] = *reinterpret_cast<const float4 *>(src + (size_t)r * ld + col);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + 16 * q;
+        tile[r][c4 + 0] = v[q].x; tile[r][c4 + 1] = v[q].y; tile[r][c4 + 2] = v[q].z; tile[r][c4 + 3] = v[q].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int lr = r0 + 16 * q;
+        const int row = bq * 64 + lr;               // destination row (global); local row lb * 64 + lr
+        const int col = bx * 64 + c4;               // destination columns col .. col + 3
+        if (row >= n) continue;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = tile[c4 + e][lr];
+        float *dst = local + (size_t)(lb * 64 + lr) * ld + col;
+        if (col > row && col + 3 < n) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (col + e > row && col + e < n) dst[e] = o[e];
+        }
+    }
+}
+
+// slot of item i = (owner part << 24) | local row in that part's buffer
+__global__ void gram_row_slots_kernel(const int *__restrict__ rank_of, int n_items, int n_parts, int *__restrict__ slots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int jp = rank_of[i];
+    slots[i] = (((jp >> 6) % n_parts) << 24) | blk_local_row(jp, n_parts);
 }
 
 static int bits_for_n(long long n) { int b = 1; while ((1ll << b) < n && b < 32) ++b; return b; }
@@ -397,13 +471,19 @@ using namespace rt;
         rt::count_launch(2);                                                                       \
     } while (0)
 
-extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
-                             const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
-                             int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
-                             int32_t *d_orig_of, int32_t *h_cuts, void *stream) {
+// block_mode = 0: part owns a contiguous row slab [h_cuts[part], h_cuts[part + 1]) balanced by multiply-adds, written
+// at its global rows of an I-row buffer.  block_mode = 1: block-cyclic ownership of 64-row blocks, the buffer holds only
+// the rows of this part (blk_local_row); no cost pass, no host synchronisation, h_cuts unused.
+static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                           const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                           int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
+                           int32_t *d_orig_of, int32_t *h_cuts, int block_mode, void *stream) {
     RT_ARG(n_users > 0 && n_items > 0 && nnz >= 0 && nnz < (1ll << 31), "shape");
     RT_ARG(n_parts >= 1 && part >= 0 && part < n_parts, "part / n_parts");
-    RT_ARG(d_cptr && d_rptr && d_Gp && ldgp >= n_items && d_rank_of && d_orig_of && h_cuts, "null pointer / ldgp");
+    RT_ARG(d_cptr && d_rptr && d_Gp && ldgp >= n_items && d_rank_of && d_orig_of && (h_cuts || block_mode), "null pointer / ldgp");
+    int32_t cuts_dummy[RT_MAX_PEERS + 2];
+    if (block_mode) { RT_ARG(n_parts <= RT_MAX_PEERS, "n_parts"); h_cuts = cuts_dummy; }
+    const int blk_parts = block_mode ? n_parts : 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int bs = 256;
     const int I = n_items;
@@ -463,17 +543,18 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
         int rc = rt_csr_split(n_users, d_rptr, P.pidx, 0, RW, R, P.hseg, stream);
         if (rc) return rc;
     }
-    if (n_parts > 1) RT_CUDA(cudaMemsetAsync(P.cost, 0, sizeof(unsigned long long) * ((size_t)I + 1), st));
+    const bool by_cost = n_parts > 1 && !block_mode;
+    if (by_cost) RT_CUDA(cudaMemsetAsync(P.cost, 0, sizeof(unsigned long long) * ((size_t)I + 1), st));
     entry_pos_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(I, nnz, d_rank_of, d_cptr, d_cidx, d_rptr, P.pidx, P.cpos,
-                                                                    n_parts > 1 ? P.cost : nullptr);
+                                                                    by_cost ? P.cost : nullptr);
     RT_CHECK_LAUNCH();
-    chunk_count_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(I, d_orig_of, d_cptr, P.n_chunks);
+    chunk_count_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(I, d_orig_of, d_cptr, P.n_chunks, blk_parts, part);
     RT_CHECK_LAUNCH();
     RT_CUDA(cudaMemsetAsync(P.n_chunks + I, 0, sizeof(int), st));
     G3_CUB(cub::DeviceScan::ExclusiveSum(d_tmp__, tmp_bytes__, P.n_chunks, P.chunk_start, I + 1, st));
     // ---- partition of the rows by exact work -------------------------------------------------------
     int row_begin = 0, row_end = I;
-    if (n_parts > 1) {
+    if (by_cost) {
         G3_CUB(cub::DeviceScan::InclusiveSum(d_tmp__, tmp_bytes__, P.cost, P.cost_s, I, st));
         std::vector<unsigned long long> cs((size_t)I);
         RT_CUDA(cudaMemcpyAsync(cs.data(), P.cost_s, sizeof(unsigned long long) * (size_t)I, cudaMemcpyDeviceToHost, st));
@@ -502,7 +583,7 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
             RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             gram_lower_kernel<SL><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
                                                                     d_orig_of, d_cptr, d_cidx, d_cval, P.cpos, P.hseg,    \
-                                                                    P.pidx, P.pval, d_Gp, ldgp, P.counter);              \
+                                                                    P.pidx, P.pval, d_Gp, ldgp, P.counter, blk_parts);   \
         } while (0)
         if (RW == 1152) G3_LAUNCH(1152);
         else if (RW == 2304) G3_LAUNCH(2304);
@@ -511,6 +592,22 @@ extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_
         RT_CHECK_LAUNCH();
     }
     return RT_OK;
+}
+
+extern "C" int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                             const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
+                             int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
+                             int32_t *d_orig_of, int32_t *h_cuts, void *stream) {
+    return gram_lower_impl(n_users, n_items, d_cptr, d_cidx, d_cval, d_rptr, d_ridx, d_rval, nnz, part, n_parts, d_Gp, ldgp,
+                           d_rank_of, d_orig_of, h_cuts, 0, stream);
+}
+
+extern "C" int rt_gram_lower_blocks(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                                    const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx,
+                                    const float *d_rval, int64_t nnz, int32_t part, int32_t n_parts, float *d_slab,
+                                    int64_t ldgp, int32_t *d_rank_of, int32_t *d_orig_of, void *stream) {
+    return gram_lower_impl(n_users, n_items, d_cptr, d_cidx, d_cval, d_rptr, d_ridx, d_rval, nnz, part, n_parts, d_slab, ldgp,
+                           d_rank_of, d_orig_of, nullptr, 1, stream);
 }
 
 static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
@@ -524,7 +621,64 @@ static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, co
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_items) grid = n_items;
-    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_gram_block_rows(int32_t n_items, int32_t n_parts, int32_t part, int32_t *h_rows_alloc, int32_t *h_rows_own) {
+    RT_ARG(n_items > 0 && n_parts >= 1 && n_parts <= RT_MAX_PEERS && part >= 0 && part < n_parts, "arguments");
+    const int nt = (n_items + 63) / 64;
+    if (h_rows_alloc) *h_rows_alloc = (nt + n_parts - 1) / n_parts * 64;
+    if (h_rows_own) {
+        int own = 0;
+        for (int b = part; b < nt; b += n_parts) own += std::min(64, n_items - b * 64);
+        *h_rows_own = own;
+    }
+    return RT_OK;
+}
+
+extern "C" int rt_gram_pull_cols(int32_t n_items, const void *const *h_slabs, int32_t n_parts, int32_t part, int64_t ldgp,
+                                 void *stream) {
+    RT_ARG(n_items > 0 && h_slabs && ldgp >= n_items && (ldgp % 4) == 0, "arguments (ldgp must be a multiple of 4)");
+    RT_ARG(n_parts >= 1 && n_parts <= RT_MAX_PEERS && part >= 0 && part < n_parts, "part / n_parts");
+    GramRowPeers P;
+    for (int p = 0; p < RT_MAX_PEERS; ++p) {
+        P.src[p] = (const float *)h_slabs[p < n_parts ? p : 0];
+        RT_ARG(P.src[p] != nullptr && (((uintptr_t)P.src[p]) & 15) == 0, "slab pointers must be 16-byte aligned");
+    }
+    P.n_parts = n_parts; P.me = part;
+    const int nt = (n_items + 63) / 64;
+    const int n_local = (nt - part + n_parts - 1) / n_parts;
+    if (n_local <= 0) return RT_OK;
+    gram_pull_cols_kernel<<<dim3(nt, n_local), 256, 0, (cudaStream_t)stream>>>(P, (float *)h_slabs[part], n_items, ldgp);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_gram_unpermute_rows(int32_t n_rows, int32_t n_items, const float *d_slab, int64_t ldgp,
+                                      const int32_t *d_rank_of, float *d_rows, int64_t ldg, void *stream) {
+    RT_ARG(n_rows >= 0 && n_items > 0 && d_slab && d_rank_of && d_rows && ldgp >= n_items && ldg >= n_items && d_rows != d_slab,
+           "arguments");
+    if (n_rows == 0) return RT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t row_bytes = sizeof(float) * (size_t)n_items;
+    const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
+    const size_t smem = stage ? row_bytes : 0;
+    RT_CUDA(cudaFuncSetAttribute(gram_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = stage ? (int)((size_t)(rt::smem_optin() + 1024) / (smem + 1024)) : 2;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    int grid = rt::sm_count() * per_sm;
+    if (grid > n_rows) grid = n_rows;
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_slab, ldgp, n_rows, n_items, d_rank_of, nullptr, d_rows, ldg, stage);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+extern "C" int rt_gram_row_slots(int32_t n_items, const int32_t *d_rank_of, int32_t n_parts, int32_t *d_slots, void *stream) {
+    RT_ARG(n_items > 0 && n_items < (1 << 24) && d_rank_of && d_slots && n_parts >= 1 && n_parts <= RT_MAX_PEERS, "arguments");
+    gram_row_slots_kernel<<<(n_items + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_rank_of, n_items, n_parts, d_slots);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -22,6 +22,11 @@ namespace rt {
 
 struct SolveArgs {
     const float *G;
+    // owner-rows layout of the multi-GPU fit (rt_slim_solve_rows): row i of G lives in buffer rowslot[i] >> 24 (own
+    // memory or a CUDA IPC mapping of a peer GPU, read over NVLink) at local row rowslot[i] & 0xffffff.  rowslot ==
+    // nullptr: one dense matrix G.
+    const float *bases[RT_MAX_PEERS];
+    const int *rowslot;
     const float *diag;  // G[i][i] gathered contiguously
     int64_t ldg;
     int n_items;
@@ -48,6 +53,14 @@ struct SolveArgs {
     int hot_in_smem;  // per-visit arrays live in dynamic shared memory
     int use_gs;       // dense live x live Gram block cached in shared memory (nn mode)
 };
+
+__device__ __forceinline__ const float *g_row(const SolveArgs &A, int i) {
+    if (A.rowslot) {
+        const int s = __ldg(A.rowslot + i);
+        return A.bases[s >> 24] + (size_t)(s & 0xffffff) * A.ldg;
+    }
+    return A.G + (size_t)i * A.ldg;
+}
 
 struct Misc {
     FastSelScratch fsel;
@@ -116,8 +129,6 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
     int *cidx = (int *)take(cold, co, sizeof(int) * NU);
     unsigned char *excl = (unsigned char *)take(cold, co, NU);
 
-    const float *G = A.G;
-    const int64_t ld = A.ldg;
 
     for (;;) {
         __syncthreads();
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
         if (t >= A.n_targets) break;
         if (A.only_flagged && !A.only_flagged[t]) continue;
         const int j = A.targets[t];
-        const float *gj = G + (size_t)j * ld;
+        const float *gj = g_row(A, j);
 
         // ---- universe ------------------------------------------------------------------------
         if (nnmode) {
@@ -180,13 +191,13 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
         if (A.use_gs) {
             for (int e = tid; e < m * m; e += NT) {
                 const int r = e / m, c = e - r * m;
-                Gs[e] = G[(size_t)F(live[r]) * ld + F(live[c])];
+                Gs[e] = g_row(A, F(live[r]))[F(live[c])];
             }
             __syncthreads();
         }
         // G entry between two live slots
         auto GL = [&](int sr, int sc) -> double {
-            return A.use_gs ? (double)Gs[sr * m + sc] : (double)G[(size_t)F(live[sr]) * ld + F(live[sc])];
+            return A.use_gs ? (double)Gs[sr * m + sc] : (double)g_row(A, F(live[sr]))[F(live[sc])];
         };
 
         int n_active = 0, n_iter = 0, n_gap = 0, draws = 0;
@@ -228,7 +239,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
                         double hk = 0.0;
                         for (int e = 0; e < ns; ++e) {
                             const int sc = list[e];
-                            hk += (double)G[(size_t)F(live[sc]) * ld + f] * w[sc];
+                            hk += (double)g_row(A, F(live[sc]))[f] * w[sc];
                         }
                         v = (double)gj[f] - hk;
                     }
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
     const float *G = A.G;
     const int64_t ld = A.ldg;
     const int N = A.n_items;
-    const bool vec4 = ((ld & 3) == 0) && ((((uintptr_t)G) & 15) == 0);
+    const bool vec4 = ((ld & 3) == 0) && (A.rowslot != nullptr || (((uintptr_t)G) & 15) == 0);  // row buffers are 16-byte aligned
 
     for (;;) {
         int t = 0;
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= A.n_targets) break;
         const int j = A.targets[t];
-        const float *gj = G + (size_t)j * ld;
+        const float *gj = g_row(A, j);
         __syncwarp();
 
         // ---- candidates ------------------------------------------------------------------------------
@@ -666,7 +677,7 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
                         while (r * (r + 1) / 2 > e) --r;
                         while ((r + 1) * (r + 2) / 2 <= e) ++r;
                         rr[q] = r; cc[q] = e - r * (r + 1) / 2;
-                        v[q] = __ldg(G + (size_t)S->feat[S->live[r]] * ld + S->feat[S->live[cc[q]]]);
+                        v[q] = __ldg(g_row(A, S->feat[S->live[r]]) + S->feat[S->live[cc[q]]]);
                     }
                 }
 #pragma unroll
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
                     if (f == j) v = 0.0;
                     else {
                         // row f of the symmetric G at the support columns: ns independent loads, four in flight
-                        const float *gf = G + (size_t)f * ld;
+                        const float *gf = g_row(A, f);
                         double hk = 0.0;
                         int e = 0;
                         for (; e + 3 < ns; e += 4) {
@@ -854,9 +865,9 @@ __global__ void count_flags_kernel(const int *__restrict__ flags, int n, int *__
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
 }
 
-__global__ void gather_diag_kernel(const float *G, int64_t ld, int n, float *diag) {
+__global__ void gather_diag_kernel(SolveArgs A, int n, float *diag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) diag[i] = G[(size_t)i * ld + i];
+    if (i < n) diag[i] = g_row(A, i)[i];
 }
 
 // ---- xorshift32 table -------------------------------------------------------------------------
@@ -957,11 +968,12 @@ SolvePlan make_plan(int n_items, int nn, int n_targets) {
 }
 }  // namespace
 
-extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, const int32_t *d_targets,
-                             int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
-                             const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
-                             int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
-                             int64_t *h_needed, int32_t *d_stats, void *stream) {
+static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t n_bases, const int32_t *d_rowslot,
+                           int64_t ldg, int32_t n_items, const int32_t *d_targets,
+                           int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
+                           const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
+                           int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                           int64_t *h_needed, int32_t *d_stats, void *stream) {
     RT_ARG(cfg != nullptr, "cfg");
     RT_ARG(n_items > 0 && ldg >= n_items, "n_items/ldg");
     RT_ARG(n_targets >= 0, "n_targets");
@@ -969,7 +981,7 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
     RT_ARG(cfg->alpha * cfg->l1_ratio > 0.0, "alpha*l1_ratio must be > 0 (L1 penalty; gap-safe screening path)");
     if (h_needed) *h_needed = 0;
     if (n_targets == 0) return RT_OK;
-    RT_ARG(d_G && d_targets && d_rng && d_out_off && d_out_cnt && d_out_rows && d_out_vals, "null pointer");
+    RT_ARG((d_G || d_rowslot) && d_targets && d_rng && d_out_off && d_out_cnt && d_out_rows && d_out_vals, "null pointer");
     SolvePlan p = make_plan(n_items, cfg->nn, n_targets);
     RT_ARG(rng_len >= (int64_t)cfg->max_iter * p.NU + 64, "rng table too short");
     const size_t diag_bytes = rt::align_up((size_t)n_items * sizeof(float));
@@ -979,7 +991,9 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
     cudaStream_t st = (cudaStream_t)stream;
 
     SolveArgs A;
-    A.G = d_G; A.ldg = ldg; A.n_items = n_items; A.targets = d_targets; A.n_targets = n_targets;
+    A.G = d_G; A.rowslot = d_rowslot;
+    for (int q = 0; q < RT_MAX_PEERS; ++q) A.bases[q] = d_rowslot ? (const float *)h_bases[q < n_bases ? q : 0] : d_G;
+    A.ldg = ldg; A.n_items = n_items; A.targets = d_targets; A.n_targets = n_targets;
     A.nn = cfg->nn; A.NU = p.NU; A.sel_in = d_sel_in; A.sel_out = d_sel_out;
     A.a = (double)(float)(cfg->alpha * cfg->l1_ratio * (double)cfg->n_samples);
     A.b = (double)(float)(cfg->alpha * (1.0 - cfg->l1_ratio) * (double)cfg->n_samples);
@@ -989,14 +1003,15 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
     A.out_vals = d_out_vals; A.out_cap = out_cap; A.stats = d_stats;
     A.cursor = (unsigned long long *)d_workspace;
     float *d_diag = (float *)((char *)d_workspace + 1024);
-    A.diag = d_diag;
     A.scratch = (char *)d_workspace + 1024 + diag_bytes;
     A.scratch_per_cta = p.scratch_per_cta;
     A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
     A.only_flagged = nullptr;
     A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;
     RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
-    gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(d_G, ldg, n_items, d_diag);
+    A.diag = nullptr;
+    gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(A, n_items, d_diag);
+    A.diag = d_diag;
     RT_CHECK_LAUNCH();
     bool block_pass = true;
     if (cfg->nn > 0 && p.NU <= SW_MAXU && rt::option(rt::OPT_SOLVE_IMPL) != 1) {
@@ -1045,4 +1060,25 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
         return RT_ERR_CAPACITY;
     }
     return RT_OK;
+}
+
+extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, const int32_t *d_targets,
+                             int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
+                             const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
+                             int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                             int64_t *h_needed, int32_t *d_stats, void *stream) {
+    RT_ARG(d_G != nullptr || n_targets == 0, "null pointer");
+    return slim_solve_impl(d_G, nullptr, 0, nullptr, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len, d_sel_out,
+                           d_out_off, d_out_cnt, d_out_rows, d_out_vals, out_cap, h_needed, d_stats, stream);
+}
+
+extern "C" int rt_slim_solve_rows(const void *const *h_bases, int32_t n_bases, const int32_t *d_rowslot, int64_t ldg,
+                                  int32_t n_items, const int32_t *d_targets, int32_t n_targets, const rt_fit_config *cfg,
+                                  const int32_t *d_sel_in, const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out,
+                                  int64_t *d_out_off, int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals,
+                                  int64_t out_cap, int64_t *h_needed, int32_t *d_stats, void *stream) {
+    RT_ARG(h_bases && n_bases >= 1 && n_bases <= RT_MAX_PEERS && d_rowslot && (ldg % 4) == 0, "row buffers");
+    for (int q = 0; q < n_bases; ++q) RT_ARG(h_bases[q] != nullptr && (((uintptr_t)h_bases[q]) & 15) == 0, "row buffer pointers");
+    return slim_solve_impl(nullptr, h_bases, n_bases, d_rowslot, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len,
+                           d_sel_out, d_out_off, d_out_cnt, d_out_rows, d_out_vals, out_cap, h_needed, d_stats, stream);
 }

@@ -241,6 +241,61 @@ def gram_finish_p2p(L: GramLower, slab_ptrs: Sequence[int], part: int, n_items: 
     return out
 
 
+def gram_block_rows(n_items: int, n_parts: int, part: int = 0) -> Tuple[int, int]:
+    """(rows_alloc, rows_own) of the block-cyclic owner-rows layout (rt_gram_block_rows)."""
+    ra, ro = C.c_int32(0), C.c_int32(0)
+    check(_lib.load().rt_gram_block_rows(int(n_items), int(n_parts), int(part), C.byref(ra), C.byref(ro)), "rt_gram_block_rows")
+    return int(ra.value), int(ro.value)
+
+
+def gram_lower_blocks(X: DeviceMatrix, part: int, n_parts: int, slab_ptr: int):
+    """Lower-triangle part of the rows ``part`` owns (block-cyclic, rank space) into the raw buffer ``slab_ptr``
+    ([rows_alloc, slab_ld(I)] floats, zero-filled here).  Returns (rank_of, orig_of)."""
+    t = require_cuda()
+    lib = _lib.load()
+    I = X.n_items
+    ld = slab_ld(I)
+    rows_alloc, _ = gram_block_rows(I, n_parts, part)
+    check(lib.rt_memset(C.c_void_p(int(slab_ptr)), 0, 4 * rows_alloc * ld, stream_ptr()), "rt_memset")
+    rank_of = empty(I, t.int32)
+    orig_of = empty(I, t.int32)
+    check(lib.rt_gram_lower_blocks(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.rptr), ptr(X.ridx),
+                                   ptr(X.rval), X.nnz, int(part), int(n_parts), C.c_void_p(int(slab_ptr)), ld,
+                                   ptr(rank_of), ptr(orig_of), stream_ptr()), "rt_gram_lower_blocks")
+    return rank_of, orig_of
+
+
+def gram_pull_cols(slab_ptrs: Sequence[int], part: int, n_items: int) -> None:
+    """Completes the own rows: transposed pull of the triangle columns below them out of every part's slab."""
+    arr = (C.c_void_p * len(slab_ptrs))(*[C.c_void_p(int(p)) for p in slab_ptrs])
+    check(_lib.load().rt_gram_pull_cols(int(n_items), arr, len(slab_ptrs), int(part), slab_ld(n_items), stream_ptr()),
+          "rt_gram_pull_cols")
+
+
+def gram_unpermute_rows(slab_ptr: int, rows_ptr: int, n_rows: int, n_items: int, rank_of) -> None:
+    """Columns of the own rows back to item ids: rows[r][i] = slab[r][rank_of[i]]."""
+    ld = slab_ld(n_items)
+    check(_lib.load().rt_gram_unpermute_rows(int(n_rows), int(n_items), C.c_void_p(int(slab_ptr)), ld, ptr(rank_of),
+                                             C.c_void_p(int(rows_ptr)), ld, stream_ptr()), "rt_gram_unpermute_rows")
+
+
+def gram_row_slots(rank_of, n_parts: int):
+    t = require_cuda()
+    I = int(rank_of.numel())
+    slots = empty(I, t.int32)
+    check(_lib.load().rt_gram_row_slots(I, ptr(rank_of), int(n_parts), ptr(slots), stream_ptr()), "rt_gram_row_slots")
+    return slots
+
+
+def block_targets(orig_of, n_items: int, part: int, n_parts: int):
+    """Item ids of the targets ``part`` owns under the block-cyclic layout (device int32), in local-row order."""
+    t = require_cuda()
+    _, rows_own = gram_block_rows(n_items, n_parts, part)
+    l = t.arange(rows_own, dtype=t.int64, device=dev())
+    jp = ((l >> 6) * n_parts + part) * 64 + (l & 63)   # only the globally last block can be partial, and it is last here too
+    return orig_of.long()[jp].to(t.int32)
+
+
 def gram_finish(L: GramLower, out=None):
     t = require_cuda()
     I = L.Gp.shape[0]
@@ -291,8 +346,18 @@ class SolveResult:
     n_pairs: int
 
 
+@dataclass
+class GramRows:
+    """Gram matrix in the owner-rows layout of the multi-GPU fit (rt_gram_lower_blocks ... rt_gram_row_slots):
+    ``bases[p]`` = address of part p's row buffer in this process (own memory or CUDA IPC mapping), ``slots`` =
+    int32 [I] device, (owner << 24) | local row, ``ld`` = common leading dimension."""
+    bases: Sequence[int]
+    slots: object
+    ld: int
+
+
 def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool = False) -> SolveResult:
-    """Batched ElasticNet solves on the Gram matrix (K4)."""
+    """Batched ElasticNet solves on the Gram matrix (K4).  ``G``: dense [I, ld] tensor or ``GramRows``."""
     t = require_cuda()
     lib = _lib.load()
     T = int(targets.numel())
@@ -308,9 +373,15 @@ def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool 
     while True:
         rows = empty(max(cap, 1), t.int32)
         vals = empty(max(cap, 1), t.float32)
-        rc = lib.rt_slim_solve(ptr(G), G.stride(0), n_items, ptr(targets), T, C.byref(cfg), ptr(sel_in), ptr(rng),
-                               rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows), ptr(vals), cap, C.byref(needed),
-                               ptr(stats), stream_ptr())
+        if isinstance(G, GramRows):
+            arr = (C.c_void_p * len(G.bases))(*[C.c_void_p(int(b)) for b in G.bases])
+            rc = lib.rt_slim_solve_rows(arr, len(G.bases), ptr(G.slots), int(G.ld), n_items, ptr(targets), T, C.byref(cfg),
+                                        ptr(sel_in), ptr(rng), rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows),
+                                        ptr(vals), cap, C.byref(needed), ptr(stats), stream_ptr())
+        else:
+            rc = lib.rt_slim_solve(ptr(G), G.stride(0), n_items, ptr(targets), T, C.byref(cfg), ptr(sel_in), ptr(rng),
+                                   rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows), ptr(vals), cap, C.byref(needed),
+                                   ptr(stats), stream_ptr())
         if rc == _lib.RT_ERR_CAPACITY and needed.value > cap:
             cap = int(needed.value)
             continue

@@ -142,7 +142,7 @@ class PeerSlabs:
         t = D.require_cuda()
         lib = _lib.load()
         self.n_items, self.rank, self.world, self.group = n_items, rank, world, group
-        self.own, self.ptrs, self.error = 0, [0] * world, None
+        self.own, self.ptrs, self.error, self.rows_alloc = 0, [0] * world, None, 0
         self._flag = t.zeros(1, dtype=t.int32, device=D.dev())
         # every rank takes part in both collectives below whatever happens locally, so a failure on one
         # rank (IPC not permitted in this container, out of memory) turns into an agreed fallback, not a hang
@@ -150,7 +150,11 @@ class PeerSlabs:
         try:
             own = C.c_void_p(0)
             handle = (C.c_uint8 * 64)()
-            _lib.check(lib.rt_ipc_alloc(4 * n_items * D.slab_ld(n_items), C.byref(own), handle), "rt_ipc_alloc")
+            # room for the full-height slab of the triangle exchange, or for the two half-buffers of the owner-rows
+            # layout (lower slab + finished rows, rows_alloc rows each)
+            self.rows_alloc, _ = D.gram_block_rows(n_items, world, rank)
+            n_rows = max(n_items, 2 * self.rows_alloc)
+            _lib.check(lib.rt_ipc_alloc(4 * n_rows * D.slab_ld(n_items), C.byref(own), handle), "rt_ipc_alloc")
             self.own = int(own.value)
             payload = bytes(handle)
         except Exception as e:  # noqa: BLE001
@@ -193,6 +197,11 @@ class PeerSlabs:
                 import logging
                 logging.warning(f"peer-memory slab exchange unavailable ({obj.error}); using NCCL broadcasts")
         return cls._cache[key]
+
+    def rows_ptrs(self) -> list:
+        """Addresses of every part's finished-rows buffer (second half of the IPC allocation)."""
+        off = 4 * self.rows_alloc * D.slab_ld(self.n_items)
+        return [int(p) + off for p in self.ptrs]
 
     def barrier(self) -> None:
         """Stream-ordered node barrier: the one-element all-reduce completes only after every rank has
@@ -238,6 +247,35 @@ def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchan
     G = D.gram_finish(L)
     mark("gram_finish")
     return G
+
+
+def fit_owner_rows(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int, world: int, group=None, want_sel: bool = False,
+                   marks=None, slabs: Optional[PeerSlabs] = None):
+    """Multi-GPU fit without a full Gram exchange: every rank computes the lower-triangle part of the Gram rows it
+    owns (block-cyclic in popularity-rank space), completes them by pulling the transposed columns below them out of
+    the peers' slabs over NVLink (``rt_gram_pull_cols``: (N-1)/N^2 of the matrix per GPU), and solves its own targets;
+    the few Gram entries between candidates that live in other ranks' rows are gathered from peer memory inside the
+    solver.  Returns this rank's ``SolveResult`` (targets = the items of its blocks) or ``None`` when CUDA IPC is not
+    usable on this node (agreed by every rank; the caller falls back to ``fit_sharded``)."""
+    mark = marks if marks is not None else (lambda name: None)
+    slabs = slabs if slabs is not None else PeerSlabs.get(X.n_items, rank, world, group)
+    if slabs is None:
+        return None
+    I = X.n_items
+    slabs.barrier()   # nobody is still reading this rank's buffers (pulls / solver gathers of the previous fit)
+    rank_of, orig_of = D.gram_lower_blocks(X, rank, world, slabs.own)
+    mark("gram_lower")
+    slabs.barrier()   # every lower slab is complete
+    D.gram_pull_cols(slabs.ptrs, rank, I)
+    rows = slabs.rows_ptrs()
+    D.gram_unpermute_rows(slabs.own, rows[rank], slabs.rows_alloc, I, rank_of)
+    G = D.GramRows(rows, D.gram_row_slots(rank_of, world), D.slab_ld(I))
+    tg = D.block_targets(orig_of, I, rank, world)
+    mark("gram_rows")
+    slabs.barrier()   # every rank's rows are complete
+    res = D.solve(G, I, tg, cfg, want_sel=want_sel)
+    mark("solve")
+    return res
 
 
 def fit_sharded(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int = 0, world: int = 1, group=None,

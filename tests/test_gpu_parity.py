@@ -165,6 +165,83 @@ def test_gram_fused_pull_mirror_equals_single_pass():
             lib.rt_ipc_free(C.c_void_p(b))
 
 
+@pytest.mark.parametrize("n_parts", [1, 2, 3, 8])
+def test_gram_owner_rows_equals_single_pass(n_parts):
+    """The owner-rows layout of the multi-GPU fit on one GPU: n_parts slabs in separate buffers (standing in for the
+    IPC mappings of peer ranks), run in lock step like the real ranks -- everybody rt_gram_lower_blocks, (barrier),
+    everybody rt_gram_pull_cols + rt_gram_unpermute_rows, (barrier), everybody rt_slim_solve_rows on its own targets.
+    Every assembled row equals the row of the single-pass Gram matrix bit for bit, the union of the parts' targets is
+    every item exactly once, and the solver output (candidates, coefficients, sweep counts) through the row slots
+    equals the single-GPU solve on the dense matrix, for the warp kernel (nn = 20), the CTA kernel (all features on a
+    sampled target list) and with items that nobody rated (all-zero rows)."""
+    import ctypes as C
+    import torch
+    from rtrec_b200 import _lib, device as D
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    lib = _lib.load()
+    U, I, N = 2500, 1777, 120000          # 28 blocks of 64 rows, the last one partial
+    u, i, ts, r = synth_events(U, I, N, seed=9, rating="int")
+    i = np.random.default_rng(2).permutation(I)[i]
+    keep = (i % 89) != 3
+    X = sp.csc_matrix((r[keep].astype(np.float32), (u[keep], i[keep])), shape=(U, I))
+    dX = D.DeviceMatrix.from_scipy(X)
+    G_ref = D.gram_full(dX)
+    ld = D.slab_ld(I)
+    rows_alloc, _ = D.gram_block_rows(I, n_parts, 0)
+    slabs = []
+    row_bufs = [torch.empty((rows_alloc, ld), dtype=torch.float32, device="cuda") for _ in range(n_parts)]
+    rows = [int(b.data_ptr()) for b in row_bufs]
+    try:
+        for p in range(n_parts):
+            ptr_, h = C.c_void_p(0), (C.c_uint8 * 64)()
+            _lib.check(lib.rt_ipc_alloc(4 * rows_alloc * ld, C.byref(ptr_), h), "rt_ipc_alloc")
+            slabs.append(int(ptr_.value))
+        ro = [D.gram_lower_blocks(dX, p, n_parts, slabs[p]) for p in range(n_parts)]
+        for p in range(n_parts):
+            assert torch.equal(ro[p][0], ro[0][0]) and torch.equal(ro[p][1], ro[0][1])
+        rank_of, orig_of = ro[0]
+        for p in range(n_parts):
+            D.gram_pull_cols(slabs, p, I)
+        for p in range(n_parts):
+            D.gram_unpermute_rows(slabs[p], rows[p], rows_alloc, I, rank_of)
+        slots = D.gram_row_slots(rank_of, n_parts)
+        torch.cuda.synchronize()
+        # rows: G_ref[i] == buffer[slot >> 24][slot & 0xffffff]
+        sl = slots.cpu().numpy()
+        Gr = G_ref.cpu().numpy()
+        bufs = [b.cpu().numpy() for b in row_bufs]
+        got = np.stack([bufs[s >> 24][s & 0xffffff, :I] for s in sl])
+        assert np.array_equal(got, Gr)
+        # targets: a partition of the items
+        tgs = [D.block_targets(orig_of, I, p, n_parts) for p in range(n_parts)]
+        allt = np.concatenate([x.cpu().numpy() for x in tgs])
+        assert np.array_equal(np.sort(allt), np.arange(I))
+        GR = D.GramRows(rows, slots, ld)
+        for nn, sample in ((20, None), (None, 40)):
+            cfg = SLIMElastic({"nn_feature_selection": nn} if nn else {})._config(dX)
+            for p in range(n_parts):
+                tg = tgs[p] if sample is None else tgs[p][:: max(1, int(tgs[p].numel()) // sample)].contiguous()
+                a = D.solve(G_ref, I, tg, cfg, want_sel=nn is not None)
+                b = D.solve(GR, I, tg, cfg, want_sel=nn is not None)
+                assert torch.equal(a.cnt, b.cnt) and torch.equal(a.stats, b.stats)
+                if nn is not None:
+                    n = int(a.n_pairs)
+                    assert torch.equal(a.off, b.off) and torch.equal(a.sel, b.sel)
+                    assert torch.equal(a.rows[:n], b.rows[:n]) and torch.equal(a.vals[:n], b.vals[:n])
+                else:
+                    # all-features mode appends each column at an atomic cursor: compare column by column
+                    ao, bo, cn = a.off.cpu().numpy(), b.off.cpu().numpy(), a.cnt.cpu().numpy()
+                    ar, br = a.rows.cpu().numpy(), b.rows.cpu().numpy()
+                    av, bv = a.vals.cpu().numpy(), b.vals.cpu().numpy()
+                    for q in range(len(cn)):
+                        assert np.array_equal(ar[ao[q]:ao[q] + cn[q]], br[bo[q]:bo[q] + cn[q]])
+                        assert np.array_equal(av[ao[q]:ao[q] + cn[q]], bv[bo[q]:bo[q] + cn[q]])
+    finally:
+        D.torch().cuda.synchronize()
+        for b in slabs:
+            lib.rt_ipc_free(C.c_void_p(b))
+
+
 # ------------------------------------------------------------------------------------------ fit
 @pytest.mark.parametrize("name,cfg", FIT_CASES)
 def test_fit_matches_reference_golden(golden, name, cfg):

@@ -127,3 +127,24 @@ def test_every_referenced_helper_exists():
             if (a or b) not in _lib.PROTOTYPES:
                 missing.append((os.path.relpath(f, ROOT), a or b))
     assert not missing, missing
+
+
+@pytest.mark.parametrize("n_items,n_parts", [(1, 1), (63, 2), (64, 2), (65, 8), (1777, 3), (26744, 8), (105542, 5)])
+def test_block_cyclic_row_ownership(n_items, n_parts):
+    """Geometry of the owner-rows multi-GPU fit (rt_gram_block_rows; pure host code, no GPU): the 64-row blocks of
+    the rank-space matrix are dealt round-robin, every part's buffer has the same height, the real rows of all parts
+    add up to the catalogue, and the local-row -> global-row map used for the target lists is a bijection."""
+    from rtrec_b200 import device as D
+    nt = (n_items + 63) // 64
+    seen = []
+    for part in range(n_parts):
+        rows_alloc, rows_own = D.gram_block_rows(n_items, n_parts, part)
+        assert rows_alloc == -(-nt // n_parts) * 64 and rows_own <= rows_alloc
+        l = np.arange(rows_own, dtype=np.int64)
+        jp = ((l >> 6) * n_parts + part) * 64 + (l & 63)
+        assert (jp < n_items).all()
+        assert (((jp >> 6) % n_parts) == part).all()
+        assert np.array_equal((((jp >> 6) // n_parts) << 6) | (jp & 63), l)   # blk_local_row
+        seen.append(jp)
+    allj = np.concatenate(seen)
+    assert np.array_equal(np.sort(allj), np.arange(n_items))
