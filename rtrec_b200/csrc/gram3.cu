@@ -75,7 +75,7 @@ __global__ void low32_kernel(const unsigned long long *__restrict__ keys, int64_
 // the exact multiply-add count of every rank-column (sum of prefix lengths) for the multi-GPU partition
 __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict__ rank_of, const int *__restrict__ cptr,
                                  const int *__restrict__ cidx, const int *__restrict__ rptr, const int *__restrict__ pidx,
-                                 int *__restrict__ cpos, unsigned long long *__restrict__ cost) {
+                                 int *__restrict__ cpos, unsigned long long *__restrict__ cost, int blk_parts, int blk_me) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = e < nnz;
     int jp = -1;
@@ -85,6 +85,8 @@ __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict
         int lo = 0, hi = n_items;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cptr[mid] <= (int)e) lo = mid; else hi = mid; }
         jp = rank_of[lo];
+        // block-cyclic mode: positions are only needed for the columns this part owns (cost == nullptr there)
+        if (blk_parts > 0 && ((jp >> 6) % blk_parts) != blk_me) return;
         const int u = cidx[e];
         const int a = rptr[u];
         int l2 = a, h2 = rptr[u + 1];
@@ -546,7 +548,7 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
     const bool by_cost = n_parts > 1 && !block_mode;
     if (by_cost) RT_CUDA(cudaMemsetAsync(P.cost, 0, sizeof(unsigned long long) * ((size_t)I + 1), st));
     entry_pos_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(I, nnz, d_rank_of, d_cptr, d_cidx, d_rptr, P.pidx, P.cpos,
-                                                                    by_cost ? P.cost : nullptr);
+                                                                    by_cost ? P.cost : nullptr, blk_parts, part);
     RT_CHECK_LAUNCH();
     chunk_count_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(I, d_orig_of, d_cptr, P.n_chunks, blk_parts, part);
     RT_CHECK_LAUNCH();

@@ -234,7 +234,13 @@ class BaseModel(ABC):
 
     @classmethod
     def load(cls, f: FileLike):
-        return cls._deserialize(pickle.loads(f.read()))
+        """Reads a model file written by ``save`` -- of this package or of the reference implementation
+        (rtrec.models.*.save): reference objects are rebuilt as this package's (utils/refpickle.py)."""
+        from ..utils import refpickle
+        data = refpickle.loads(f.read())
+        if isinstance(data, dict):
+            data = {k: refpickle.convert(v) for k, v in data.items()}
+        return cls._deserialize(data)
 
     @classmethod
     def loads(cls, data: bytes):

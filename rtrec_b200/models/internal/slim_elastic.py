@@ -73,6 +73,11 @@ class SLIMElastic:
         self._W = None
         self._W_host = None if W is None else sp.csc_matrix(W, dtype=np.float32)
 
+    def _set_host_similarity(self, W: sp.spmatrix) -> None:
+        """Take over a fitted W from the host (a model file written by the reference: scipy CSC, float64 after a
+        serial ``fit`` -- the values were computed in float32 by the solver, so the cast is exact)."""
+        self.item_similarity = W
+
     def _device_W(self) -> Optional[D.DeviceW]:
         if self._W is None and self._W_host is not None:
             self._W = D.DeviceW.from_scipy(self._W_host)

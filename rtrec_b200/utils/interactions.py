@@ -211,6 +211,26 @@ class UserItemInteractions:
             self._pend.append((a[:, 0].astype(np.int32), a[:, 1].astype(np.int32), a[:, 2].copy(), a[:, 3].copy()))
             self._pend_scalar = []
 
+    def _load_host_state(self, keys: np.ndarray, vals: np.ndarray, stamps: np.ndarray, *, max_user_id: int, max_item_id: int,
+                         max_timestamp: float, all_item_ids: set, hot_items: Optional[LRUFreqSet] = None) -> None:
+        """Replace the store contents with sorted (user << 32 | item, value, stamp) columns held on the host; they are
+        uploaded when a GPU is first needed, exactly like an unpickled store.  Used by utils/refpickle.py to take over
+        the dict-of-dicts of a model file written by the reference (interactions.py:26)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        assert len(keys) == len(vals) == len(stamps)
+        assert len(keys) < 2 or bool((keys[1:] > keys[:-1]).all()), "store keys must be strictly ascending"
+        self._keys = self._vals = self._stamps = None
+        self._host_state = (keys, np.ascontiguousarray(vals, dtype=np.float64), np.ascontiguousarray(stamps, dtype=np.float64))
+        self._n_pairs = len(keys)
+        self._pend, self._pend_scalar, self._pend_n, self._pend_upsert = [], [], 0, None
+        self.max_user_id, self.max_item_id, self.max_timestamp = int(max_user_id), int(max_item_id), float(max_timestamp)
+        self._dev_max_ts = float(max_timestamp)
+        self.all_item_ids = set(int(x) for x in all_item_ids)
+        if hot_items is not None:
+            self.hot_items = hot_items
+        self._matrix_cache = {}
+        self.version += 1
+
     def _ensure_device_state(self) -> None:
         if self._host_state is not None:
             k, v, s = self._host_state
