@@ -53,6 +53,11 @@ class SLIMElastic:
         self.nn_feature_selection = config.get("nn_feature_selection", None)
         if self.nn_feature_selection is not None:
             assert int(self.nn_feature_selection) > 0, f"n_neighbors must be a positive integer: {self.nn_feature_selection}"
+        # SPMD multi-GPU mode (not in the reference): with ``distributed=True`` and an initialised torch.distributed
+        # process group (one process per GPU, every rank making the same calls with the same data), fits are sharded
+        # by item column (pipeline.fit_owner_rows) and bulk scoring by query user; every rank ends up with the full W
+        # and returns the full result, so the API reads exactly like the single-GPU one.
+        self.distributed = bool(config.get("distributed", False))
         self._W: Optional[D.DeviceW] = None
         self._W_host: Optional[sp.csc_matrix] = None  # lazy mirror / pending upload
         self.last_fit_stats: Optional[np.ndarray] = None
@@ -107,18 +112,38 @@ class SLIMElastic:
             return D.DeviceMatrix.from_scipy(interaction_matrix)
         raise ValueError(err)
 
+    def _dist_ctx(self):
+        """(rank, world) when the SPMD multi-GPU mode is active, else None."""
+        if not getattr(self, "distributed", False):
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+            return None
+        return dist.get_rank(), dist.get_world_size()
+
     def _fit_device(self, X: D.DeviceMatrix, targets: np.ndarray, keep_old: bool, sel_in: Optional[np.ndarray] = None):
         """gram -> solve -> merge.  ``targets``: item ids (host int array)."""
         t = D.require_cuda()
         cfg = self._config(X)
         n_items = X.n_items
         tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
-        G = D.gram_full(X) if X.nnz > 0 else D.gram(X)
-        sel_dev = None
-        if sel_in is not None and cfg.nn > 0:
-            sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))
-        res = D.solve(G, n_items, tg, cfg, sel_in=sel_dev, want_sel=self.keep_fit_details)
-        del G
+        res = None
+        ctx = self._dist_ctx()
+        if ctx is not None and X.nnz > 0 and sel_in is None:
+            # item-sharded fit: this rank solves the targets of its own Gram row blocks; the solver outputs (a few
+            # MB) are all-gathered so that every rank assembles the same full W
+            from ... import pipeline as P
+            part = P.fit_owner_rows(X, cfg, rank=ctx[0], world=ctx[1], targets=tg if len(targets) != n_items else None)
+            if part is not None:
+                res = P.gather_solve_results(part, ctx[1])
+                targets = res.targets.cpu().numpy()
+        if res is None:
+            G = D.gram_full(X) if X.nnz > 0 else D.gram(X)
+            sel_dev = None
+            if sel_in is not None and cfg.nn > 0:
+                sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))
+            res = D.solve(G, n_items, tg, cfg, sel_in=sel_dev, want_sel=self.keep_fit_details)
+            del G
         old = self._device_W() if keep_old else None
         self._W = D.w_merge(old, n_items, res)
         self._W_host = None
@@ -246,6 +271,16 @@ class SLIMElastic:
         k = max(1, min(int(top_k), 128))
         mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
         users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
+        ctx = self._dist_ctx()
+        if ctx is not None and Q >= 64 * ctx[1]:
+            # query-sharded scoring: every rank scores its slice of the users, the finished lists are all-gathered
+            from ... import pipeline as P
+            ids, _, cnt = P.recommend_query_sharded(X, users, W, k, filter_interacted, mode, rank=ctx[0], world=ctx[1])
+            rows = ids.cpu().numpy().tolist()
+            c = cnt.cpu().numpy()
+            for r in np.flatnonzero(c < k).tolist():
+                del rows[r][int(c[r]):]
+            return rows
         pin = _PINNED.get("lists")
         if pin is None or pin[0].numel() < Q * k or pin[1].numel() < Q:
             pin = (t.empty(Q * k, dtype=t.int32, pin_memory=True), t.empty(Q, dtype=t.int32, pin_memory=True))

@@ -250,13 +250,14 @@ def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchan
 
 
 def fit_owner_rows(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int, world: int, group=None, want_sel: bool = False,
-                   marks=None, slabs: Optional[PeerSlabs] = None):
+                   marks=None, slabs: Optional[PeerSlabs] = None, targets=None):
     """Multi-GPU fit without a full Gram exchange: every rank computes the lower-triangle part of the Gram rows it
     owns (block-cyclic in popularity-rank space), completes them by pulling the transposed columns below them out of
     the peers' slabs over NVLink (``rt_gram_pull_cols``: (N-1)/N^2 of the matrix per GPU), and solves its own targets;
     the few Gram entries between candidates that live in other ranks' rows are gathered from peer memory inside the
-    solver.  Returns this rank's ``SolveResult`` (targets = the items of its blocks) or ``None`` when CUDA IPC is not
-    usable on this node (agreed by every rank; the caller falls back to ``fit_sharded``)."""
+    solver.  Returns this rank's ``SolveResult`` (targets = the items of its blocks, restricted to ``targets`` -- a
+    device int32 list, the same on every rank -- when given) or ``None`` when CUDA IPC is not usable on this node
+    (agreed by every rank; the caller falls back to ``fit_sharded``)."""
     mark = marks if marks is not None else (lambda name: None)
     slabs = slabs if slabs is not None else PeerSlabs.get(X.n_items, rank, world, group)
     if slabs is None:
@@ -271,6 +272,9 @@ def fit_owner_rows(X: D.DeviceMatrix, cfg: FitConfig, *, rank: int, world: int, 
     D.gram_unpermute_rows(slabs.own, rows[rank], slabs.rows_alloc, I, rank_of)
     G = D.GramRows(rows, D.gram_row_slots(rank_of, world), D.slab_ld(I))
     tg = D.block_targets(orig_of, I, rank, world)
+    if targets is not None:
+        t = D.torch()
+        tg = tg[t.isin(tg, targets)].contiguous()
     mark("gram_rows")
     slabs.barrier()   # every rank's rows are complete
     res = D.solve(G, I, tg, cfg, want_sel=want_sel)

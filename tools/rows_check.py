@@ -81,6 +81,20 @@ for nn in (50, None):
         ok = same_w(W, W1)
         say(f"nn={nn}: whole-triangle exchange W equal to the single-GPU W = {ok}")
         assert ok
+# ---- the public API in SPMD mode: SLIM(distributed=True) on every rank against an ordinary single-GPU model
+from rtrec_b200.models import SLIM
+users = list(range(U)) + [U + 5]          # + a cold user
+out = {}
+for flag in (False, True):
+    m = SLIM(nn_feature_selection=50, distributed=flag)
+    m.add_interaction_arrays(u, i, ts, r.astype(np.float64))
+    m.bulk_fit()
+    out[flag] = (m.recommend_batch(users, top_k=10), m.model.item_similarity)
+    say(f"API distributed={flag}: fitted, nnz(W) = {out[flag][1].nnz}")
+dW = (out[False][1] != out[True][1]).nnz
+same = sum(int(a == b) for a, b in zip(out[False][0], out[True][0]))
+say(f"API: W entries differing = {dW}, identical top-10 lists = {same}/{len(users)}")
+assert dW == 0 and same == len(users)
 dist.barrier()
 say("done")
 dist.destroy_process_group()
