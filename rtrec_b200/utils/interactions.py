@@ -41,6 +41,9 @@ class UserItemInteractions:
         self.max_user_id = 0
         self.max_item_id = 0
         self.max_timestamp = 0.0
+        # SPMD multi-GPU mode (see SLIMElastic.distributed): every rank is handed the same event batch, so each rank
+        # uploads only its 1/N slice over its own PCIe link and the slices are all-gathered over NVLink
+        self.distributed = bool(kwargs.get("distributed", False))
         # device state (torch tensors) -- sorted by key
         self._keys = None
         self._vals = None
@@ -153,12 +156,40 @@ class UserItemInteractions:
         lib = _lib.load()
         n = len(u)
         # pageable host columns -> device through the library's threaded staging pipeline (ids narrowed to int32)
-        du, di = D.empty(n, t.int32), D.empty(n, t.int32)
-        dts, dd = D.empty(n, t.float64), D.empty(n, t.float64)
         lo_u, hi_u, lo_i, hi_i, mx_ts = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_double(0)
-        _lib.check(lib.rt_upload_events(u.ctypes.data, i.ctypes.data, ts.ctypes.data, d.ctypes.data, n, D.ptr(du), D.ptr(di),
-                                        D.ptr(dts), D.ptr(dd), C.byref(lo_u), C.byref(hi_u), C.byref(lo_i), C.byref(hi_i),
-                                        C.byref(mx_ts), 0, D.stream_ptr()), "rt_upload_events")
+        ctx = self._dist_ctx()
+        if ctx is None:
+            du, di = D.empty(n, t.int32), D.empty(n, t.int32)
+            dts, dd = D.empty(n, t.float64), D.empty(n, t.float64)
+            _lib.check(lib.rt_upload_events(u.ctypes.data, i.ctypes.data, ts.ctypes.data, d.ctypes.data, n, D.ptr(du), D.ptr(di),
+                                            D.ptr(dts), D.ptr(dd), C.byref(lo_u), C.byref(hi_u), C.byref(lo_i), C.byref(hi_i),
+                                            C.byref(mx_ts), 0, D.stream_ptr()), "rt_upload_events")
+        else:
+            # this rank's slice [a, b) of the batch goes up its own PCIe link; NCCL all-gathers the slices and the id
+            # ranges / max timestamp (the host never touches the other N-1 slices)
+            import torch.distributed as dist
+            rank, world = ctx
+            per = -(-n // world)
+            a, b = min(n, rank * per), min(n, (rank + 1) * per)
+            m = b - a
+            su, si = D.zeros(per, t.int32), D.zeros(per, t.int32)
+            sts, sd = D.zeros(per, t.float64), D.zeros(per, t.float64)
+            if m > 0:
+                _lib.check(lib.rt_upload_events(u[a:b].ctypes.data, i[a:b].ctypes.data, ts[a:b].ctypes.data, d[a:b].ctypes.data,
+                                                m, D.ptr(su), D.ptr(si), D.ptr(sts), D.ptr(sd), C.byref(lo_u), C.byref(hi_u),
+                                                C.byref(lo_i), C.byref(hi_i), C.byref(mx_ts), 0, D.stream_ptr()),
+                           "rt_upload_events")
+            big = float(1 << 40)
+            ext = t.tensor([-(lo_u.value if m else big), hi_u.value if m else -big, -(lo_i.value if m else big),
+                            hi_i.value if m else -big, mx_ts.value if m else -big], dtype=t.float64, device=D.dev())
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX)
+            fu, fi = D.empty(per * world, t.int32), D.empty(per * world, t.int32)
+            fts, fd = D.empty(per * world, t.float64), D.empty(per * world, t.float64)
+            for full, part in ((fu, su), (fi, si), (fts, sts), (fd, sd)):
+                dist.all_gather_into_tensor(full, part)
+            du, di, dts, dd = fu[:n], fi[:n], fts[:n], fd[:n]
+            e = ext.tolist()
+            lo_u.value, hi_u.value, lo_i.value, hi_i.value, mx_ts.value = int(-e[0]), int(e[1]), int(-e[2]), int(e[3]), e[4]
         if lo_u.value < 0 or lo_i.value < 0 or hi_u.value > _INT32_MAX or hi_i.value > _INT32_MAX:
             raise ValueError("ids outside [0, 2^31): the device store indexes with int32")
         imax = int(hi_i.value)
@@ -175,6 +206,15 @@ class UserItemInteractions:
             self.hot_items.add_batch(i[pos] if not pos.all() else i)
         self.all_item_ids.update(np.flatnonzero(seen_h).tolist())
         return self._queue_device_batch(du, di, dts, dd, upsert, int(hi_u.value), imax, float(mx_ts.value), None, None)
+
+    def _dist_ctx(self):
+        """(rank, world) when the SPMD multi-GPU mode is active, else None."""
+        if not getattr(self, "distributed", False):
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+            return None
+        return dist.get_rank(), dist.get_world_size()
 
     def _queue_device_batch(self, du, di, dts, dd, upsert: bool, umax: int, imax: int, ts_max: float,
                             host_items: Optional[np.ndarray], host_delta: Optional[np.ndarray]) -> bool:
