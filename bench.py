@@ -334,10 +334,18 @@ def run_ours(args):
     kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0), solve_bytes), "recommend": (rec_ms, rec_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9
+    traffic = None
+    if world == 1 and args.workload == "ml20m":
+        try:   # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same workload
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_ml20m.json"))).get(dom)
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kern[dom][1], "ms_per_launch": round(kern[dom][0], 3),
-                "note": "gram = rt_gram_lower + rt_gram_finish (rank/sort/prefix kernels included); bytes per SURVEY.md 8(d)"}
+                "note": "bytes per SURVEY.md 8(d); gram = every kernel of the Gram phase (rank/sort/prefix kernels included); "
+                        "recommend: W (a few MB) stays in L2, so the algorithmic-byte rate can exceed the HBM peak -- "
+                        "traffic (ncu DRAM bytes per launch) shows what actually reaches HBM, see DESIGN.md section 4"}
     other = {k: {"ms": round(v[0], 3), "GBps": round(v[1] / (v[0] / 1e3) / 1e9, 1) if v[0] > 0 else None} for k, v in kern.items()}
 
     # ---- e2e through the public API with host buffers.  N > 1: every rank makes the same calls on the same DataFrame
