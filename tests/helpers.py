@@ -76,6 +76,40 @@ def assert_w_parity(W_a, W_b, cols=None, max_flip_frac=0.02, what="W", X=None, a
     return rel
 
 
+def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-5, alpha=0.1, l1_ratio=0.1, tol=1e-4, what="W"):
+    """Parity bar at the full ML-20M shape, where the reference's own float32 residual arithmetic is the limit.
+
+    Measured with the CPU model of the device algorithm against the exact port of the reference on this shape
+    (tools/c2_parity_cpu.py, profiles/r2k_c2_parity_cpu.log): columns whose largest coefficient is >= 1e-3 agree to
+    <= 2e-5 of it; below that the reference computes ``w = (tmp - a) / (norm2 + b)`` with ``tmp`` ~ ``a`` = 1385, so the
+    float32 rounding of ``tmp`` (~1e-4 absolute) is 1e-4..1e-2 of ``tmp - a``: its coefficients jitter by that much from
+    sweep to sweep, the ``d_w_max / w_max <= tol`` gate opens by chance (8 sweeps where exact arithmetic needs 2), and
+    1e-4 of the column maximum is below the reference's own noise.  So:
+      * columns with max |w| >= ``big``: <= 1e-4 of the column maximum (the north_star bar), no exceptions;
+      * the others: absolute error <= ``abs_tol`` (coefficients there are < 1e-3) and, when the relative error exceeds
+        1e-4, both columns must be solutions sklearn accepts -- ElasticNet objectives within 1 % of tol*||y||^2 of each
+        other, a hundred times tighter than the solver's own stopping criterion."""
+    rel = column_errors(W_a, W_b, cols)
+    A = sp.csc_matrix(W_a, dtype=np.float64); B = sp.csc_matrix(W_b, dtype=np.float64)
+    Xc = sp.csc_matrix(X)
+    report = []
+    for j in [int(c) for c in cols]:
+        b = B.data[B.indptr[j]:B.indptr[j + 1]]
+        a = A.data[A.indptr[j]:A.indptr[j + 1]]
+        scale = max(np.abs(b).max() if len(b) else 0.0, np.abs(a).max() if len(a) else 0.0)
+        if scale >= big:
+            assert rel[j] <= W_TOL, f"{what}: column {j} (max coefficient {scale:.3e}) differs by {rel[j]:.3e} of it"
+            continue
+        assert rel[j] * scale <= abs_tol, f"{what}: column {j} absolute error {rel[j] * scale:.3e} > {abs_tol}"
+        if rel[j] > W_TOL:
+            pa, yy = enet_objective(Xc, j, np.asarray(A[:, j].todense()).ravel(), alpha, l1_ratio)
+            pb, _ = enet_objective(Xc, j, np.asarray(B[:, j].todense()).ravel(), alpha, l1_ratio)
+            report.append((j, scale, rel[j], abs(pa - pb) / (tol * yy)))
+            assert abs(pa - pb) <= 0.01 * tol * yy, (f"{what}: column {j} differs by {rel[j]:.3e} and the objectives "
+                                                     f"{pa:.9g} / {pb:.9g} differ by more than 0.01*tol*yy = {0.01 * tol * yy:.3g}")
+    return rel, report
+
+
 def topk_consistent(ids, scores_row, k, eligible_mask, tol=1e-5):
     """ids is a valid top-k of scores_row over eligible items, up to score ties within tol."""
     elig = np.flatnonzero(eligible_mask)

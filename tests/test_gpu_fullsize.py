@@ -5,7 +5,9 @@ fit cannot be replayed on the CPU inside a test).
 
   store    CSR and CSC hold the same 20M entries, canonical (sorted, no duplicates), bit-equal to the folded events
   fit      W >= 0, zero diagonal, <= nn entries per column, every entry's row is a co-rated item;
-           sampled columns within the parity bar of tests/helpers.py against the oracle (same candidates)
+           sampled columns within the at-scale parity bar of tests/helpers.py against the oracle (same candidates):
+           1e-4 of the column maximum wherever that maximum is >= 1e-3, absolute 1e-5 + equal ElasticNet objectives
+           where the reference's own float32 noise exceeds 1e-4 of a tiny column (tools/c2_parity_cpu.py)
   scoring  every list: <= 10 items, no interacted item, no duplicates, scores descending and > 0 (int ids -> sparse
            semantics); sampled users: valid top-10 of the oracle's scores; an order-independent checksum of all lists
            is reproduced by a second pass in one launch instead of chunks
@@ -16,7 +18,7 @@ import scipy.sparse as sp
 
 from oracle import slim_oracle as so
 from oracle.synth import synth_shape
-from tests.helpers import assert_w_parity, topk_consistent
+from tests.helpers import assert_w_parity_at_scale, topk_consistent
 
 pytestmark = pytest.mark.gpu
 
@@ -69,7 +71,7 @@ def test_c2_fit_full_size(c2):
     for j, (rows, vals) in zip(cols, res):
         so.SlimOracle._apply(colsd, int(j), rows, vals)
     Wo = so.SlimOracle._to_csc(colsd, I)
-    assert_w_parity(W, Wo, cols=cols, what="W at ML-20M shape", X=Xc)
+    assert_w_parity_at_scale(W, Wo, cols, Xc, what="W at ML-20M shape")
     # every neighbour is co-rated with its target (its Gram entry is positive): check on the sampled columns
     Xb = (Xc != 0).astype(np.float32)
     for j in cols:
