@@ -4,7 +4,7 @@
 // safe_sparse_dot + per-user python top-k), :743-779 and :781-818, like score.cu / score2.cu, with
 // the same results bit for bit (same fp32 summation order per score: ascending source item).
 //
-// Why a third generation (profiles/r1g_*, r1j_*): at the ML-20M shape 99 % of the multiply-adds of
+// Why a third generation (profiles/r1g_*, r1l_*): at the ML-20M shape 99 % of the multiply-adds of
 // X.W come from the ~50 most popular source items, whose W rows hold thousands of entries (they are
 // a nearest neighbour of a quarter of all targets).  v2 streams those rows as (column, value) CSR
 // pairs and scatters into the shared-memory score tile: two global loads per entry and a
@@ -13,7 +13,8 @@
 // slot `lane` only ever holds a column with (column - tile start) mod 32 == lane:
 //     * the tile update of a group is bank-conflict free by construction,
 //     * one 8-byte load per entry ((column, value) interleaved) instead of two 4-byte loads,
-//     * groups of a row are independent, so every warp keeps four loads in flight.
+//     * groups of a row are independent, so every warp keeps eight loads in flight and applies them as one
+//       batch (read-all / add / write-all, no LDS -> STS chain).
 // Rows are still applied one after the other in ascending item order (one barrier per row), light
 // rows exactly as in v2, so each score is the same fp32 sum scipy's csr_matmat produces.
 //

@@ -2,9 +2,11 @@
 
 This is the layer ``UserItemInteractions`` / ``SLIM`` sit on, exposed so that callers who already
 hold event columns on the device (bench.py, the multi-GPU driver) can run the same kernels
-without the host object model.  Sharding helpers for ``torch.distributed`` live here too: item
-columns are partitioned across ranks, X is replicated, Gram rows are all-gathered (NCCL) before
-the solves, and per-rank top-k lists are all-gathered and merged by ``rt_topk_merge``.
+without the host object model.  Sharding helpers for ``torch.distributed`` live here too: X is
+replicated; the fit is partitioned by item column -- by default every rank completes only the Gram rows of
+its own targets out of peer memory (``fit_owner_rows``), alternatively the whole triangle is exchanged
+(``gram_sharded`` + ``fit_sharded``); scoring is partitioned by query user (``recommend_query_sharded``, lists
+all-gathered) or by item column (``recommend_sharded``, per-rank top-k lists merged by ``rt_topk_merge``).
 """
 from __future__ import annotations
 
