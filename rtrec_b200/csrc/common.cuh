@@ -13,7 +13,7 @@ void count_launch(int n = 1);
 int sm_count();
 int smem_optin();
 // tuning switches settable through rt_set_option(): which kernel generation serves an entry point
-enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_SOLVE_IMPL, OPT_GRAM_SLICE, OPT_GRAM_RANGES, OPT_COUNT };
+enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_SOLVE_IMPL, OPT_GRAM_SLICE, OPT_GRAM_RANGES, OPT_GRAM_ADAPT, OPT_COUNT };
 int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).

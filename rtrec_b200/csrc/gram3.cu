@@ -118,7 +118,11 @@ __global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of,
 // local row of rank-space row jp in the slab of its owner under block-cyclic ownership
 __host__ __device__ __forceinline__ int blk_local_row(int jp, int blk_parts) { return (((jp >> 6) / blk_parts) << 6) | (jp & 63); }
 
-template <int SLICE>
+// ADAPT (rt_set_option("gram_adapt", 1), off by default until measured on the GPU): the four 32-entry batches of a
+// rater's prefetch / update are guarded by warp-uniform tests on the segment length.  On the synthetic ML-20M shape
+// 48 % of the issued batch slots hold an entry (ranges 1..3: 14-28 %, most segments there are shorter than 32); with the
+// guards it would be 83 % (CPU count over the real segment lengths).
+template <int SLICE, bool ADAPT>
 __global__ void __launch_bounds__(G3_WARPS * 32)
 gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_start, int R, int RW,
                   const int *__restrict__ orig_of, const int *__restrict__ cptr, const int *__restrict__ cidx,
@@ -182,6 +186,7 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                     for (int k = 0; k < 4; ++k) {
                         const int p = n_aa + lane + 32 * k;
                         nx[k] = -1; nv[k] = 0.f;
+                        if (ADAPT && k > 0 && n_aa + 32 * k >= n_bb) continue;   // warp-uniform: nothing in this batch
                         if (p < n_bb) { nx[k] = pidx[p] - lo; nv[k] = pval[p]; }
                     }
                 };
@@ -197,8 +202,10 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                     const bool more = mask != 0u;
                     if (more) { fetch(__ffs(mask) - 1); mask &= mask - 1; }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 4; ++k) {
+                        if (ADAPT && k > 0 && aa + 32 * k >= bb) continue;       // warp-uniform
                         if (cx[k] >= 0) slice[cx[k]] = __fadd_rn(slice[cx[k]], __fmul_rn(yy, cv[k]));
+                    }
                     for (int p = aa + 128 + lane; p < bb; p += 32) {
                         const int x = pidx[p] - lo;
                         slice[x] = __fadd_rn(slice[x], __fmul_rn(yy, pval[p]));
@@ -580,16 +587,17 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         const int grid = rt::sm_count() * per_sm;
-#define G3_LAUNCH(SL)                                                                                                   \
+#define G3_LAUNCH(SL, AD)                                                                                               \
         do {                                                                                                            \
-            RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gram_lower_kernel<SL><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
-                                                                    d_orig_of, d_cptr, d_cidx, d_cval, P.cpos, P.hseg,    \
-                                                                    P.pidx, P.pval, d_Gp, ldgp, P.counter, blk_parts);   \
+            RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gram_lower_kernel<SL, AD><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
+                                                                        d_orig_of, d_cptr, d_cidx, d_cval, P.cpos, P.hseg, \
+                                                                        P.pidx, P.pval, d_Gp, ldgp, P.counter, blk_parts); \
         } while (0)
-        if (RW == 1152) G3_LAUNCH(1152);
-        else if (RW == 2304) G3_LAUNCH(2304);
-        else G3_LAUNCH(G3_SLICE);
+        const bool adapt = rt::option(rt::OPT_GRAM_ADAPT) != 0;
+        if (RW == 1152) { if (adapt) G3_LAUNCH(1152, true); else G3_LAUNCH(1152, false); }
+        else if (RW == 2304) { if (adapt) G3_LAUNCH(2304, true); else G3_LAUNCH(2304, false); }
+        else { if (adapt) G3_LAUNCH(G3_SLICE, true); else G3_LAUNCH(G3_SLICE, false); }
 #undef G3_LAUNCH
         RT_CHECK_LAUNCH();
     }

@@ -4,6 +4,8 @@ Bars (BASELINE.json north_star 6): indices / bookkeeping / store matrices bit-ex
 of the column's largest coefficient (columns whose stop decision flips by one sweep: 1e-3, at most
 2 % of columns); top-k lists equal up to score ties.
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -240,6 +242,23 @@ def test_gram_owner_rows_equals_single_pass(n_parts):
         D.torch().cuda.synchronize()
         for b in slabs:
             lib.rt_ipc_free(C.c_void_p(b))
+
+
+@pytest.mark.skipif(os.environ.get("RTREC_B200_EXPERIMENTAL") != "1", reason="experimental kernel variants (not yet measured on the GPU)")
+def test_gram_adaptive_variant_equals_default():
+    """rt_set_option("gram_adapt", 1): same Gram matrix bit for bit (only empty 32-entry batches are skipped)."""
+    from rtrec_b200 import device as D
+    U, I, N = 2500, 1777, 120000
+    u, i, ts, r = synth_events(U, I, N, seed=9, rating="cont")
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    dX = D.DeviceMatrix.from_scipy(X)
+    G0 = D.gram_full(dX).cpu().numpy()
+    try:
+        D.set_option("gram_adapt", 1)
+        G1 = D.gram_full(dX).cpu().numpy()
+    finally:
+        D.set_option("gram_adapt", 0)
+    assert np.array_equal(G0, G1)
 
 
 # ------------------------------------------------------------------------------------------ fit
