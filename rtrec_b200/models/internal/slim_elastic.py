@@ -335,10 +335,52 @@ class SLIMElastic:
         ids, scores, cnt = D.similar(W, items, max(1, int(top_k)))
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
 
-    # ------------------------------------------------------------------ not on the SLIM hot path
-    def predict(self, *a, **k):
-        self._require_fitted("predict")
-        raise NotImplementedError("dense score export (predict*, slim_elastic.py:566-626) is not part of the accelerated path; use recommend*")
+    # ------------------------------------------------------------------ dense score export (slim_elastic.py:566-626)
+    # Not called by SLIM / Recommender (nor by anything else in the reference package); served by the candidate
+    # scoring kernel (rt_slim_recommend_candidates: every candidate is returned with its score), 128 columns per launch.
+    def _scores_device(self, user_ids: np.ndarray, X: D.DeviceMatrix, item_ids=None, what: str = "predict") -> np.ndarray:
+        W = self._require_fitted(what)
+        if X.n_items != W.n_items:
+            raise ValueError(f"dimension mismatch: interaction matrix has {X.n_items} items, W has {W.n_items}")
+        user_ids = np.ascontiguousarray(user_ids, dtype=np.int64)
+        if len(user_ids) and (user_ids.min() < 0 or user_ids.max() >= X.n_users):
+            raise IndexError("row index out of range")
+        cols = np.arange(W.n_items, dtype=np.int32) if item_ids is None else np.ascontiguousarray(item_ids, dtype=np.int32)
+        if len(cols) and (cols.min() < 0 or cols.max() >= W.n_items):
+            raise IndexError("column index out of range")
+        Q = len(user_ids)
+        out = np.zeros((Q, len(cols)), dtype=np.float32)
+        if Q == 0 or len(cols) == 0:
+            return out
+        users = D.to_dev(user_ids.astype(np.int32))
+        rows = np.arange(Q)[:, None]
+        for a in range(0, len(cols), 128):
+            chunk = cols[a:a + 128]
+            pos, sc, cnt = D.recommend_candidates(X, users, W, D.to_dev(chunk), len(chunk))
+            pos, sc, cnt = pos.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+            assert (cnt == len(chunk)).all(), "candidate scoring returns every candidate"
+            out[rows, a + pos] = sc
+        return out
 
-    predict_selected = predict
-    predict_all = predict
+    @staticmethod
+    def _shape_scores(S: np.ndarray, dense_output: bool):
+        return S if dense_output else sp.csr_matrix(S)   # exact zeros are not stored, like scipy's csr_matmat result
+
+    def predict(self, user_id: int, interaction_matrix, dense_output: bool = True):
+        """slim_elastic.py:566-586: scores of one user over all items, shape (1, n_items)."""
+        self._require_fitted("predict")
+        X = self._as_device(interaction_matrix, allow=("csr",), err="Interaction matrix must be a scipy.sparse.csr_matrix.")
+        return self._shape_scores(self._scores_device(np.asarray([user_id]), X, None, "predict"), dense_output)
+
+    def predict_selected(self, user_id: int, item_ids: List[int], interaction_matrix, dense_output: bool = True):
+        """slim_elastic.py:588-608: scores of one user over ``item_ids``, shape (1, len(item_ids))."""
+        self._require_fitted("predict_selected")
+        X = self._as_device(interaction_matrix, allow=("csr",), err="Interaction matrix must be a scipy.sparse.csr_matrix.")
+        return self._shape_scores(self._scores_device(np.asarray([user_id]), X, item_ids, "predict_selected"), dense_output)
+
+    def predict_all(self, interaction_matrix, dense_output: bool = True):
+        """slim_elastic.py:610-626: scores of every user over all items, shape (n_users, n_items) -- a dense matrix, as in
+        the reference; meant for small matrices."""
+        self._require_fitted("predict_all")
+        X = self._as_device(interaction_matrix, allow=("csr",), err="Interaction matrix must be a scipy.sparse.csr_matrix.")
+        return self._shape_scores(self._scores_device(np.arange(X.n_users), X, None, "predict_all"), dense_output)

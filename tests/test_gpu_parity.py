@@ -261,6 +261,29 @@ def test_gram_adaptive_variant_equals_default():
     assert np.array_equal(G0, G1)
 
 
+@pytest.mark.skipif(os.environ.get("RTREC_B200_EXPERIMENTAL") != "1", reason="added after the round's GPU budget was spent; first run is due in round 2")
+def test_predict_family_matches_scipy(golden):
+    """predict / predict_selected / predict_all (slim_elastic.py:566-626) against scipy on the golden W: same float32
+    sums (ascending source item), dense and sparse output forms, errors as in the reference."""
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    z = golden("slim_nn20_cont")
+    X = csc_from(z, "X0").tocsr().astype(np.float32)
+    W = w_from(z, "W0").astype(np.float32)
+    m = SLIMElastic({"nn_feature_selection": 20})
+    with pytest.raises(RuntimeError, match="Model must be fitted"):
+        m.predict(0, X)
+    m.item_similarity = W
+    S = np.asarray((X @ W).todense(), dtype=np.float32)
+    assert np.array_equal(m.predict_all(X), S)
+    assert np.array_equal(m.predict(3, X), S[3:4])
+    ids = [5, 0, 17, 5, 2]
+    assert np.array_equal(m.predict_selected(3, ids, X), S[3:4][:, ids])
+    sp_out = m.predict(3, X, dense_output=False)
+    assert sp.issparse(sp_out) and np.array_equal(np.asarray(sp_out.todense()), S[3:4])
+    with pytest.raises(IndexError):
+        m.predict(X.shape[0], X)
+
+
 # ------------------------------------------------------------------------------------------ fit
 @pytest.mark.parametrize("name,cfg", FIT_CASES)
 def test_fit_matches_reference_golden(golden, name, cfg):
