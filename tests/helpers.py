@@ -85,7 +85,8 @@ def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-5, alpha=0.
     float32 rounding of ``tmp`` (~1e-4 absolute) is 1e-4..1e-2 of ``tmp - a``: its coefficients jitter by that much from
     sweep to sweep, the ``d_w_max / w_max <= tol`` gate opens by chance (8 sweeps where exact arithmetic needs 2), and
     1e-4 of the column maximum is below the reference's own noise.  So:
-      * columns with max |w| >= ``big``: <= 1e-4 of the column maximum (the north_star bar), no exceptions;
+      * columns with max |w| >= ``big``: the bar of :func:`assert_w_parity` -- <= 1e-4 of the column maximum (north_star),
+        except for at most 2 % "flip" columns (one side ran a sweep longer), which must agree to 1e-3 or have equal objectives;
       * the others: absolute error <= ``abs_tol`` (coefficients there are < 1e-3) and, when the relative error exceeds
         1e-4, both columns must be solutions sklearn accepts -- ElasticNet objectives within 1 % of tol*||y||^2 of each
         other, a hundred times tighter than the solver's own stopping criterion."""
@@ -93,20 +94,32 @@ def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-5, alpha=0.
     A = sp.csc_matrix(W_a, dtype=np.float64); B = sp.csc_matrix(W_b, dtype=np.float64)
     Xc = sp.csc_matrix(X)
     report = []
+    n_big = n_flip = 0
+
+    def objectives_equal(j):
+        pa, yy = enet_objective(Xc, j, np.asarray(A[:, j].todense()).ravel(), alpha, l1_ratio)
+        pb, _ = enet_objective(Xc, j, np.asarray(B[:, j].todense()).ravel(), alpha, l1_ratio)
+        return abs(pa - pb) <= 0.01 * tol * yy, abs(pa - pb) / max(tol * yy, 1e-300)
+
     for j in [int(c) for c in cols]:
         b = B.data[B.indptr[j]:B.indptr[j + 1]]
         a = A.data[A.indptr[j]:A.indptr[j + 1]]
         scale = max(np.abs(b).max() if len(b) else 0.0, np.abs(a).max() if len(a) else 0.0)
+        if rel[j] <= W_TOL:
+            n_big += int(scale >= big)
+            continue
         if scale >= big:
-            assert rel[j] <= W_TOL, f"{what}: column {j} (max coefficient {scale:.3e}) differs by {rel[j]:.3e} of it"
+            n_big += 1
+            n_flip += 1
+            ok, ratio = (True, 0.0) if rel[j] <= W_TOL_FLIP else objectives_equal(j)
+            report.append((j, scale, rel[j], ratio))
+            assert ok, f"{what}: column {j} (max coefficient {scale:.3e}) differs by {rel[j]:.3e} of it and the objectives differ"
             continue
         assert rel[j] * scale <= abs_tol, f"{what}: column {j} absolute error {rel[j] * scale:.3e} > {abs_tol}"
-        if rel[j] > W_TOL:
-            pa, yy = enet_objective(Xc, j, np.asarray(A[:, j].todense()).ravel(), alpha, l1_ratio)
-            pb, _ = enet_objective(Xc, j, np.asarray(B[:, j].todense()).ravel(), alpha, l1_ratio)
-            report.append((j, scale, rel[j], abs(pa - pb) / (tol * yy)))
-            assert abs(pa - pb) <= 0.01 * tol * yy, (f"{what}: column {j} differs by {rel[j]:.3e} and the objectives "
-                                                     f"{pa:.9g} / {pb:.9g} differ by more than 0.01*tol*yy = {0.01 * tol * yy:.3g}")
+        ok, ratio = objectives_equal(j)
+        report.append((j, scale, rel[j], ratio))
+        assert ok, f"{what}: column {j} differs by {rel[j]:.3e} of {scale:.3e} and the objectives differ by {ratio:.3e} of tol*yy"
+    assert n_flip <= max(1, int(0.02 * max(n_big, 1))), f"{what}: {n_flip} of {n_big} columns with coefficients >= {big} above {W_TOL}"
     return rel, report
 
 
