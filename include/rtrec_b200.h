@@ -394,8 +394,8 @@ int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d
 
 /* Tuning switches: "score_impl" for rt_slim_recommend (1 = first-generation scoring kernel,
  * 2 = staged/pipelined kernel, default 2; the packed third generation has its own entry point);
- * "gram_impl", "gram_slice", "gram_ranges", "gram_adapt" (1 = segment-length guards in gram_lower_kernel, experimental,
- * default 0) for the Gram kernels;
+ * "gram_impl", "gram_slice", "gram_ranges", "gram_adapt" (experimental variants of gram_lower_kernel, default 0:
+ * 1 = segment-length guards, 2 = guards + packed (relative index, value) entries) for the Gram kernels;
  * "solve_impl" for rt_slim_solve (1 = one CTA per target column for every configuration, 2 = one warp
  * per target column when nn <= 64, default 2; 3 = like 2 but every 7th target is handed to the CTA
  * kernel, a test hook for the overflow fallback).  Returns RT_ERR_ARG for an unknown name. */

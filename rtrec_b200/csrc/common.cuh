@@ -18,7 +18,7 @@ int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).
 void *scratch(int slot, size_t bytes);
-enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_SLOTS };
+enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_GRAM_PACK, SCR_SLOTS };
 
 #define RT_CUDA(expr)                                                                              \
     do {                                                                                           \

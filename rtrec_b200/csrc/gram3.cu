@@ -71,6 +71,16 @@ __global__ void low32_kernel(const unsigned long long *__restrict__ keys, int64_
     if (i < n) out[i] = (int)(keys[i] & 0xffffffffull);
 }
 
+// packed view of the rank-sorted rows for gram_lower_kernel<.., 2>: (rank - base of the range that holds it, value bits)
+__global__ void pack_entries_kernel(const int *__restrict__ pidx, const float *__restrict__ pval, int64_t n, int RW, int R,
+                                    int2 *__restrict__ pent) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int rank = pidx[i];
+    const int g = min(rank / RW, R);
+    pent[i] = make_int2(rank - g * RW, __float_as_int(pval[i]));
+}
+
 // one thread per stored entry e = (u, j): position of rank(j) inside the rank-sorted row of u; optionally
 // the exact multiply-add count of every rank-column (sum of prefix lengths) for the multi-GPU partition
 __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict__ rank_of, const int *__restrict__ cptr,
@@ -118,17 +128,24 @@ __global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of,
 // local row of rank-space row jp in the slab of its owner under block-cyclic ownership
 __host__ __device__ __forceinline__ int blk_local_row(int jp, int blk_parts) { return (((jp >> 6) / blk_parts) << 6) | (jp & 63); }
 
-// ADAPT (rt_set_option("gram_adapt", 1), off by default until measured on the GPU): the four 32-entry batches of a
-// rater's prefetch / update are guarded by warp-uniform tests on the segment length.  On the synthetic ML-20M shape
-// 48 % of the issued batch slots hold an entry (ranges 1..3: 14-28 %, most segments there are shorter than 32); with the
-// guards it would be 83 % (CPU count over the real segment lengths).
-template <int SLICE, bool ADAPT>
+// MODE (rt_set_option("gram_adapt", m), 0 by default until the variants are measured on the GPU):
+//   1  the four 32-entry batches of a rater's prefetch / update are guarded by warp-uniform tests on the segment length.
+//      On the synthetic ML-20M shape 48 % of the issued batch slots hold an entry (ranges 1..3: 14-28 %, most segments
+//      there are shorter than 32); with the guards it would be 83 % (CPU count over the real segment lengths, DESIGN.md
+//      section 8);
+//   2  as 1, and the rank-sorted rows are read as packed (index relative to the entry's own range, value) pairs
+//      (`pent`, written by pack_entries_kernel): one 8-byte load and one address computation per entry instead of two,
+//      no subtraction of the range base (~12 instead of ~16 instructions per batch slot).
+// Every mode produces the same matrix bit for bit (same multiply-adds in the same order).
+template <int SLICE, int MODE>
 __global__ void __launch_bounds__(G3_WARPS * 32)
 gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_start, int R, int RW,
                   const int *__restrict__ orig_of, const int *__restrict__ cptr, const int *__restrict__ cidx,
                   const float *__restrict__ cval, const int *__restrict__ cpos, const int *__restrict__ hseg,
                   const int *__restrict__ pidx, const float *__restrict__ pval, float *__restrict__ Gp, int64_t ld,
-                  unsigned long long *__restrict__ counter, int blk_parts) {
+                  unsigned long long *__restrict__ counter, int blk_parts, const int2 *__restrict__ pent) {
+    constexpr bool ADAPT = MODE >= 1;
+    constexpr bool PACKED = MODE == 2;
     extern __shared__ __align__(16) float g3_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *slice = g3_smem + (size_t)warp * SLICE;
@@ -187,7 +204,10 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                         const int p = n_aa + lane + 32 * k;
                         nx[k] = -1; nv[k] = 0.f;
                         if (ADAPT && k > 0 && n_aa + 32 * k >= n_bb) continue;   // warp-uniform: nothing in this batch
-                        if (p < n_bb) { nx[k] = pidx[p] - lo; nv[k] = pval[p]; }
+                        if (p < n_bb) {
+                            if constexpr (PACKED) { const int2 en = pent[p]; nx[k] = en.x; nv[k] = __int_as_float(en.y); }
+                            else { nx[k] = pidx[p] - lo; nv[k] = pval[p]; }
+                        }
                     }
                 };
                 if (mask) { fetch(__ffs(mask) - 1); mask &= mask - 1; }
@@ -207,8 +227,13 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                         if (cx[k] >= 0) slice[cx[k]] = __fadd_rn(slice[cx[k]], __fmul_rn(yy, cv[k]));
                     }
                     for (int p = aa + 128 + lane; p < bb; p += 32) {
-                        const int x = pidx[p] - lo;
-                        slice[x] = __fadd_rn(slice[x], __fmul_rn(yy, pval[p]));
+                        if constexpr (PACKED) {
+                            const int2 en = pent[p];
+                            slice[en.x] = __fadd_rn(slice[en.x], __fmul_rn(yy, __int_as_float(en.y)));
+                        } else {
+                            const int x = pidx[p] - lo;
+                            slice[x] = __fadd_rn(slice[x], __fmul_rn(yy, pval[p]));
+                        }
                     }
                     __syncwarp();
                     if (!more) break;
@@ -238,7 +263,12 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
                     const float yy = __shfl_sync(0xffffffffu, y, src);
                     const int aa = __shfl_sync(0xffffffffu, a, src);
                     const int bb = __shfl_sync(0xffffffffu, b, src);
-                    for (int p = aa + (lane & 7); p < bb; p += 8) atomicAdd(g_row + pidx[p], __fmul_rn(yy, pval[p]));
+                    for (int p = aa + (lane & 7); p < bb; p += 8) {
+                        if constexpr (PACKED) {
+                            const int2 en = pent[p];   // index relative to the tail range
+                            atomicAdd(g_row + (size_t)R * RW + en.x, __fmul_rn(yy, __int_as_float(en.y)));
+                        } else atomicAdd(g_row + pidx[p], __fmul_rn(yy, pval[p]));
+                    }
                 }
             }
         }
@@ -587,17 +617,30 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
         const int grid = rt::sm_count() * per_sm;
-#define G3_LAUNCH(SL, AD)                                                                                               \
+        const int mode = rt::option(rt::OPT_GRAM_ADAPT);
+        int2 *pent = nullptr;
+        if (mode == 2) {
+            pent = (int2 *)rt::scratch(SCR_GRAM_PACK, sizeof(int2) * ((size_t)nnz + 64));
+            if (!pent) return RT_ERR_CUDA;
+            pack_entries_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(P.pidx, P.pval, nnz, RW, R, pent);
+            RT_CHECK_LAUNCH();
+        }
+#define G3_LAUNCH(SL, MD)                                                                                               \
         do {                                                                                                            \
-            RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            gram_lower_kernel<SL, AD><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
+            RT_CUDA(cudaFuncSetAttribute(gram_lower_kernel<SL, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            gram_lower_kernel<SL, MD><<<grid, G3_WARPS * 32, smem, st>>>(row_begin, row_end, P.chunk_start + row_begin, R, RW, \
                                                                         d_orig_of, d_cptr, d_cidx, d_cval, P.cpos, P.hseg, \
-                                                                        P.pidx, P.pval, d_Gp, ldgp, P.counter, blk_parts); \
+                                                                        P.pidx, P.pval, d_Gp, ldgp, P.counter, blk_parts, \
+                                                                        pent);                                           \
         } while (0)
-        const bool adapt = rt::option(rt::OPT_GRAM_ADAPT) != 0;
-        if (RW == 1152) { if (adapt) G3_LAUNCH(1152, true); else G3_LAUNCH(1152, false); }
-        else if (RW == 2304) { if (adapt) G3_LAUNCH(2304, true); else G3_LAUNCH(2304, false); }
-        else { if (adapt) G3_LAUNCH(G3_SLICE, true); else G3_LAUNCH(G3_SLICE, false); }
+#define G3_PICK(SL)                                                                                                     \
+        do {                                                                                                            \
+            if (mode == 2) G3_LAUNCH(SL, 2); else if (mode == 1) G3_LAUNCH(SL, 1); else G3_LAUNCH(SL, 0);               \
+        } while (0)
+        if (RW == 1152) G3_PICK(1152);
+        else if (RW == 2304) G3_PICK(2304);
+        else G3_PICK(G3_SLICE);
+#undef G3_PICK
 #undef G3_LAUNCH
         RT_CHECK_LAUNCH();
     }

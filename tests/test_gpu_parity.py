@@ -246,19 +246,22 @@ def test_gram_owner_rows_equals_single_pass(n_parts):
 
 @pytest.mark.skipif(os.environ.get("RTREC_B200_EXPERIMENTAL") != "1", reason="experimental kernel variants (not yet measured on the GPU)")
 def test_gram_adaptive_variant_equals_default():
-    """rt_set_option("gram_adapt", 1): same Gram matrix bit for bit (only empty 32-entry batches are skipped)."""
+    """rt_set_option("gram_adapt", 1 | 2): same Gram matrix bit for bit (1: empty 32-entry batches are skipped; 2: also
+    packed (relative index, value) entries), single pass and block-cyclic parts, popular head and RED tail."""
     from rtrec_b200 import device as D
-    U, I, N = 2500, 1777, 120000
+    U, I, N = 2500, 7500, 160000            # I > 4 * 1728: all four shared-memory ranges and the tail are populated
     u, i, ts, r = synth_events(U, I, N, seed=9, rating="cont")
+    i = np.random.default_rng(3).permutation(I)[i]
     X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
     dX = D.DeviceMatrix.from_scipy(X)
     G0 = D.gram_full(dX).cpu().numpy()
     try:
-        D.set_option("gram_adapt", 1)
-        G1 = D.gram_full(dX).cpu().numpy()
+        for mode in (1, 2):
+            D.set_option("gram_adapt", mode)
+            G1 = D.gram_full(dX).cpu().numpy()
+            assert np.array_equal(G0, G1), mode
     finally:
         D.set_option("gram_adapt", 0)
-    assert np.array_equal(G0, G1)
 
 
 @pytest.mark.skipif(os.environ.get("RTREC_B200_EXPERIMENTAL") != "1", reason="added after the round's GPU budget was spent; first run is due in round 2")

@@ -70,10 +70,11 @@ def main():
             res[f"gram_v3_lower_slice{sl}_r{rg}"] = {"ms": msv, "equal": bool(torch.equal(G1, G))}
         D.set_option("gram_slice", 0); D.set_option("gram_ranges", 0)
         # experimental: segment-length guards in gram_lower_kernel
-        D.set_option("gram_adapt", 1)
-        msa, _ = timeit(g3a)
-        D.gram_finish(box["L"], out=G)
-        res["gram_v3_lower_adapt"] = {"ms": msa, "equal": bool(torch.equal(G1, G))}
+        for mode in (1, 2):
+            D.set_option("gram_adapt", mode)
+            msa, _ = timeit(g3a)
+            D.gram_finish(box["L"], out=G)
+            res[f"gram_v3_lower_adapt{mode}"] = {"ms": msa, "equal": bool(torch.equal(G1, G))}
         D.set_option("gram_adapt", 0)
         D.gram_finish(D.gram_lower(X), out=G)
         res["gram_v3_equal"] = bool(torch.equal(G1, G))
