@@ -25,6 +25,10 @@ from make_golden import _import_reference, synth_events  # noqa: E402
 
 def main():
     SLIM, _ = _import_reference()
+    buf0 = io.BytesIO()
+    SLIM(n_recent_hot=7).save(buf0)                      # an unfitted model, before any event
+    with open(os.path.join(HERE, "ref_model_empty.pkl"), "wb") as f:
+        f.write(buf0.getvalue())
     cases = {
         "int": dict(kwargs=dict(nn_feature_selection=10), U=60, I=40, N=900, str_ids=False, seed=31),
         "str_decay": dict(kwargs=dict(decay_in_days=30, min_value=-2, max_value=6), U=40, I=30, N=500, str_ids=True, seed=32),

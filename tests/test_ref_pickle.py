@@ -101,3 +101,17 @@ def test_reference_pickle_serves_like_the_reference(name):
         mine = m.similar_items(q if str_ids else int(q), top_k=3, ret_scores=True)
         assert [round(s, 6) for _, s in mine] == [round(s, 6) for _, s in ref]
         assert set(x for x, _ in mine) == set(x for x, _ in ref) or len(set(s for _, s in ref)) < len(ref)
+
+
+def test_reference_pickle_of_an_unfitted_model():
+    """``SLIM(n_recent_hot=7).save`` of the reference before any event: loads as an empty, unfitted model (W is None, the
+    hot-item capacity survives), and `recommend` on it is the empty list like tests/models/test_slim.py:37-40 -- checked
+    on the host only, no device needed for an empty store."""
+    from rtrec_b200.models import SLIM
+    with open(os.path.join(GOLD, "ref_model_empty.pkl"), "rb") as f:
+        m = SLIM.load(f)
+    assert m.model.item_similarity is None
+    assert m.interactions._n_pairs == 0 and m.interactions._host_state[0].size == 0
+    assert m.interactions.hot_items.capacity == 7 and len(m.interactions.hot_items) == 0
+    assert m.interactions.max_user_id == 0 and m.interactions.max_item_id == 0
+    assert m.user_ids.pass_through is None and m.item_ids.pass_through is None
