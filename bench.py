@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 
 import numpy as np
 
-from oracle.synth import SHAPES, synth_shape
+from rtrec_b200.utils.synth import SHAPES, synth_shape
 
 WORKLOADS = {
     # name: (shape, SLIM kwargs, human description)

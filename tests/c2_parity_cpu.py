@@ -11,7 +11,7 @@ import sys, time, numpy as np, scipy.sparse as sp
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import slim_oracle as so
-from oracle.synth import synth_shape
+from rtrec_b200.utils.synth import synth_shape
 t0=time.time()
 u,i,ts,r = synth_shape("ml20m")
 U,I = int(u.max())+1, int(i.max())+1

@@ -80,7 +80,7 @@ def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-5, alpha=0.
     """Parity bar at the full ML-20M shape, where the reference's own float32 residual arithmetic is the limit.
 
     Measured with the CPU model of the device algorithm against the exact port of the reference on this shape
-    (tools/c2_parity_cpu.py, profiles/r2k_c2_parity_cpu.log): columns whose largest coefficient is >= 1e-3 agree to
+    (tests/c2_parity_cpu.py, profiles/r2k_c2_parity_cpu.log): columns whose largest coefficient is >= 1e-3 agree to
     <= 2e-5 of it; below that the reference computes ``w = (tmp - a) / (norm2 + b)`` with ``tmp`` ~ ``a`` = 1385, so the
     float32 rounding of ``tmp`` (~1e-4 absolute) is 1e-4..1e-2 of ``tmp - a``: its coefficients jitter by that much from
     sweep to sweep, the ``d_w_max / w_max <= tol`` gate opens by chance (8 sweeps where exact arithmetic needs 2), and

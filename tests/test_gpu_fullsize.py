@@ -7,7 +7,7 @@ fit cannot be replayed on the CPU inside a test).
   fit      W >= 0, zero diagonal, <= nn entries per column, every entry's row is a co-rated item;
            sampled columns within the at-scale parity bar of tests/helpers.py against the oracle (same candidates):
            1e-4 of the column maximum wherever that maximum is >= 1e-3, absolute 1e-5 + equal ElasticNet objectives
-           where the reference's own float32 noise exceeds 1e-4 of a tiny column (tools/c2_parity_cpu.py)
+           where the reference's own float32 noise exceeds 1e-4 of a tiny column (tests/c2_parity_cpu.py)
   scoring  every list: <= 10 items, no interacted item, no duplicates, scores descending and > 0 (int ids -> sparse
            semantics); sampled users: valid top-10 of the oracle's scores; an order-independent checksum of all lists
            is reproduced by a second pass in one launch instead of chunks

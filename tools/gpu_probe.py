@@ -2,7 +2,7 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from oracle.synth import synth_shape
+from rtrec_b200.utils.synth import synth_shape
 from rtrec_b200 import device as D, _lib
 from rtrec_b200.models import SLIM
 

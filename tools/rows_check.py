@@ -12,7 +12,7 @@ Prints one line per stage (flushed) so that a hang can be located.
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, scipy.sparse as sp, torch, torch.distributed as dist
-from oracle.synth import synth_events
+from rtrec_b200.utils.synth import synth_events
 from rtrec_b200 import device as D, pipeline as P
 from rtrec_b200.models.internal.slim_elastic import SLIMElastic
 
