@@ -1,7 +1,7 @@
 /*
  * gram_model.c -- single-threaded CPU MODEL of the device algorithm.  TEST INFRASTRUCTURE ONLY.
  *
- * The CUDA fit path (rtrec_b200/csrc/slim_fit.cu) does not replay sklearn's residual-form
+ * The CUDA fit path (rtrec_b200/csrc/solve.cu) does not replay sklearn's residual-form
  * coordinate descent literally; it replays the SAME coordinate sequence on the item-item Gram
  * matrix G = X^T X ("Gram-form replay").  This file states that algorithm in
  * plain C so that tests can check, without a GPU, that the reformulation agrees with the exact
