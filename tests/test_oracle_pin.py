@@ -152,3 +152,84 @@ def test_gram_form_model_all_columns_ml1m_shape():
     rel, report = assert_w_parity_at_scale(assemble(gcols), assemble(cols), tg, X, what="Gram-form model at ML-1M shape")
     assert (rel > 1e-4).sum() <= 0.005 * I
     assert (st[:, 0] != gst[:, 0]).sum() <= 0.02 * I          # sweep counts differ on well under 2 % of the columns
+
+
+def test_store_oracle_reference_known_answers():
+    """The known answers of the reference's own store tests (/root/reference/tests/utils/test_interactions.py:21-35,
+    65-116, 118-141), replayed on the oracle -- both on the event-at-a-time restatement and on the vectorised fold the
+    GPU parity tests compare against.  Wall-clock sleeps are replaced by explicit timestamps: the reference decays
+    relative to ``max_timestamp`` (= newest event + 1 s, interactions.py:99), not to the clock."""
+    now = 1.7e9
+    s = so.StoreOracle(min_value=-5, max_value=10)
+    s.add(1, 10, now, 5.0)
+    assert s.rating(1, 10) == 5.0                                     # :21-24
+    s.add(1, 10, now, 3.0)
+    assert s.rating(1, 10) == 8.0                                     # :26-30 (accumulate)
+    s.add(1, 10, now, -8.0)
+    assert s.rating(1, 10) == 0.0 and (1, 10) in s.pairs              # :32-37 (a zero stays stored)
+    assert s.rating(99, 10) == 0.0                                    # :65-67 (unknown user)
+    s.add(1, 10, now, 50.0)
+    assert s.rating(1, 10) == 10.0                                    # clip at max_value (interactions.py:105-108)
+    # decay over 7 days with decay_in_days=7: another user's event advances max_timestamp (:92-116)
+    d = so.StoreOracle(min_value=-5, max_value=10, decay_in_days=7)
+    d.add(1, 10, now - 7 * 86400, 5.0)
+    d.add(2, 10, now, 5.0)
+    factor = d.decay_rate ** (7 + 1 / 86400.0)
+    assert abs(0.5 - factor) < 0.02
+    assert abs(d.rating(1, 10) - 5.0 * factor) < 1e-12 and abs(2.5 - d.rating(1, 10)) < 0.1
+    # to_csc, full and with select_items (:118-141)
+    ev = [(0, 0, 12345, 5), (0, 1, 12346, 3), (1, 1, 12347, 4), (1, 2, 12348, 2), (2, 0, 12349, 1), (2, 2, 12350, 3)]
+    t = so.StoreOracle()
+    for u, i, ts, v in ev:
+        t.add(u, i, float(ts), float(v))
+    full = sp.csc_matrix(([5, 3, 4, 2, 1, 3], ([0, 0, 1, 1, 2, 2], [0, 1, 1, 2, 0, 2])), shape=(3, 3))
+    part = sp.csc_matrix(([3, 4, 2, 3], ([0, 1, 1, 2], [1, 1, 2, 2])), shape=(3, 3))
+    assert (t.to_csc() != full).nnz == 0 and (t.to_csc(select_items=[1, 2]) != part).nnz == 0
+    a = np.array(ev, dtype=np.float64)
+    st = so.fold_events(a[:, 0].astype(np.int64), a[:, 1].astype(np.int64), a[:, 2], a[:, 3])
+    assert (so.state_to_matrix(st, fmt="csc") != full).nnz == 0
+    assert (so.state_to_matrix(st, fmt="csc", select_items=[1, 2]) != part).nnz == 0
+    # the same decay case through the vectorised fold
+    st = so.fold_events(np.array([1, 2]), np.array([10, 10]), np.array([now - 7 * 86400, now]), np.array([5.0, 5.0]),
+                        decay_in_days=7)
+    X = so.state_to_matrix(st, decay_in_days=7, fmt="csc")
+    assert abs(float(X[1, 10]) - np.float32(5.0 * factor)) < 1e-6
+
+
+def _toy_ids(events):
+    users, items = {}, {}
+    out = []
+    for u, i, ts, r in events:
+        out.append((users.setdefault(u, len(users)), items.setdefault(i, len(items)), ts, r))
+    return out, users, items
+
+
+def test_slim_oracle_reference_known_answers():
+    """The two orderings the reference's own SLIM tests pin (/root/reference/tests/models/test_slim.py:58-79, 81-98; the
+    README example :49-73 is the second one), replayed on the oracle through the same flow as slim.py:28-43 (ingest ->
+    to_csc(item_ids) -> partial_fit_items -> similar_items / dense top-k for string ids)."""
+    now = 1.7e9
+    ev, users, items = _toy_ids([("user_1", "item_1", now, 5.0), ("user_1", "item_3", now, 4.0), ("user_1", "item_4", now, 3.0),
+                                 ("user_2", "item_1", now, 3.0), ("user_2", "item_2", now, -2.0), ("user_2", "item_4", now, 3.0),
+                                 ("user_3", "item_1", now, 4.0), ("user_3", "item_3", now, 2.0), ("user_3", "item_4", now, 4.0)])
+    name = {v: k for k, v in items.items()}
+    s = so.StoreOracle()
+    for e in ev:
+        s.add(*e)
+    o = so.SlimOracle({})
+    o.partial_fit_items(s.to_csc(select_items=sorted(set(items.values()))), sorted(set(items.values())))
+    sims = o.similar_items(items["item_1"], top_k=5)
+    assert [name[i] for i, _ in sims] == ["item_4", "item_3"] and sims[0][1] > sims[1][1]
+    # fit twice (the second pass re-adds the same events: values accumulate and clip), then recommend for user_1
+    ev, users, items = _toy_ids([("user_1", "item_1", now, 5.0), ("user_2", "item_2", now, -2.0), ("user_2", "item_1", now, 3.0),
+                                 ("user_2", "item_4", now, 3.0), ("user_1", "item_3", now, 4.0)])
+    name = {v: k for k, v in items.items()}
+    s = so.StoreOracle()
+    o = so.SlimOracle({})
+    for _ in range(2):
+        for e in ev:
+            s.add(*e)
+        o.partial_fit_items(s.to_csc(select_items=sorted(set(items.values()))), sorted(set(items.values())))
+    assert s.rating(users["user_1"], items["item_1"]) == 10.0 and s.rating(users["user_2"], items["item_2"]) == -4.0
+    rec = o.recommend_batch([users["user_1"]], s.to_csr(), top_k=5, dense_output=True)[0]
+    assert [name[i] for i in rec] == ["item_4", "item_2"]
