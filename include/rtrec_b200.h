@@ -392,10 +392,35 @@ int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d
                     const int32_t *d_items, int32_t n_query, int32_t k, int32_t *d_out_ids,
                     float *d_out_scores, int32_t *d_out_cnt, void *stream);
 
+/*
+ * Host-side replay of LRUFreqSet.add (lru.py:33-47; one call per event with delta > 0, interactions.py:115-116) for a
+ * batch in which evictions can occur: h_values[n] non-negative integer keys < key_bound in arrival order, the current set
+ * as h_in_keys / h_in_counts[n_in] in least- to most-recently-used order; the new set comes back the same way
+ * (h_out_* hold up to `capacity` entries).  Pure host code (no device work, no stream).
+ */
+int rt_lru_replay(const int64_t *h_values, int64_t n, int64_t capacity, int64_t key_bound,
+                  const int64_t *h_in_keys, const int64_t *h_in_counts, int64_t n_in,
+                  int64_t *h_out_keys, int64_t *h_out_counts, int64_t *h_n_out);
+
+/*
+ * Ranking metrics of Recommender.evaluate on device-resident top-k lists (replaces the per-user loop of
+ * recommender.py:163-200 over metrics.py:6-313: precision, recall, f1, ndcg, hit, reciprocal rank, average precision,
+ * true positives, AUC).  d_ids [n_query, k_stride] / d_cnt [n_query] = the lists as rt_slim_recommend* returns them;
+ * ground truth of query q = d_gidx[d_gptr[q] .. d_gptr[q+1]) sorted ascending (duplicates count towards its length,
+ * like len(ground_truth)); d_discount[i] = 1/log2(i+2) for i < max(recommend_size, 1) as computed by the caller.
+ * compensated_sum != 0: `sum()` over floats is CPython >= 3.12's Neumaier summation, else plain.  d_out [n_query, 9]
+ * float64 per-user values in the key order of compute_scores (precision, recall, f1, ndcg, hit_rate, mrr, map, tp,
+ * auc); each equals the Python function's result bit for bit, the caller adds them up in user order.
+ */
+int rt_eval_metrics(const int32_t *d_ids, const int32_t *d_cnt, int32_t n_query, int32_t k_stride,
+                    int32_t recommend_size, const int64_t *d_gptr, const int32_t *d_gidx,
+                    const double *d_discount, int32_t compensated_sum, double *d_out, void *stream);
+
 /* Tuning switches: "score_impl" for rt_slim_recommend (1 = first-generation scoring kernel,
  * 2 = staged/pipelined kernel, default 2; the packed third generation has its own entry point);
- * "gram_impl", "gram_slice", "gram_ranges", "gram_adapt" (experimental variants of gram_lower_kernel, default 0:
- * 1 = segment-length guards, 2 = guards + packed (relative index, value) entries) for the Gram kernels;
+ * "gram_impl", "gram_slice", "gram_ranges", "gram_adapt" (variants of gram_lower_kernel: 0 = four unconditional
+ * batches per rater, 1 = segment-length guards, 2 = guards + packed (relative index, value) entries, the default) for
+ * the Gram kernels;
  * "solve_impl" for rt_slim_solve (1 = one CTA per target column for every configuration, 2 = one warp
  * per target column when nn <= 64, default 2; 3 = like 2 but every 7th target is handed to the CTA
  * kernel, a test hook for the overflow fallback).  Returns RT_ERR_ARG for an unknown name. */

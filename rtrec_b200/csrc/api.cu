@@ -66,7 +66,7 @@ void *scratch(int slot, size_t bytes) {
     return p;
 }
 
-static int g_opts[OPT_COUNT] = {2, 2, 2, 0, 0, 0};
+static int g_opts[OPT_COUNT] = {2, 2, 2, 0, 0, 2};
 int option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_opts[key] : 0; }
 
 int sm_count() { return query_device() == RT_OK ? g_sm_count : 148; }
@@ -144,5 +144,66 @@ extern "C" int rt_ipc_free(void *d_ptr) {
 extern "C" int rt_memset(void *d_ptr, int32_t value, size_t bytes, void *stream) {
     RT_ARG(d_ptr || bytes == 0, "null pointer");
     if (bytes) RT_CUDA(cudaMemsetAsync(d_ptr, value, bytes, (cudaStream_t)stream));
+    return RT_OK;
+}
+
+// ---- host-side bookkeeping -------------------------------------------------------------------------------------
+// Sequential replay of LRUFreqSet.add (reference: /root/reference/rtrec/utils/lru.py:33-47, called per event with
+// delta > 0 from interactions.py:115-116) over an array of non-negative integer keys.  The vectorised host path of
+// rtrec_b200/utils/lru.py covers batches in which no eviction can happen; when one can (more distinct items than the
+// capacity, e.g. the 105k-item H&M catalogue against the default capacity of 100,000) the end state depends on the
+// order of every event, and the Python loop over 31M events took 9 s.  Same state machine here over dense arrays
+// (intrusive doubly linked recency list + hit counters): ~5 ns per event.  Pure host code, no device work.
+#include <vector>
+
+extern "C" int rt_lru_replay(const int64_t *h_values, int64_t n, int64_t capacity, int64_t key_bound,
+                             const int64_t *h_in_keys, const int64_t *h_in_counts, int64_t n_in,
+                             int64_t *h_out_keys, int64_t *h_out_counts, int64_t *h_n_out) {
+    RT_ARG(n >= 0 && capacity > 0 && key_bound > 0 && key_bound < (1ll << 31) && n_in >= 0 && n_in <= capacity, "sizes");
+    RT_ARG((n == 0 || h_values) && (n_in == 0 || (h_in_keys && h_in_counts)) && h_out_keys && h_out_counts && h_n_out, "null pointer");
+    const int32_t NIL = -1;
+    std::vector<int32_t> prev((size_t)key_bound, NIL), next((size_t)key_bound, NIL);
+    std::vector<int64_t> hits((size_t)key_bound, 0);     // 0 = not in the set
+    int32_t head = NIL, tail = NIL;                       // head = least recently used
+    int64_t size = 0;
+    auto push_back = [&](int32_t k) {
+        prev[k] = tail; next[k] = NIL;
+        if (tail != NIL) next[tail] = k; else head = k;
+        tail = k;
+    };
+    auto unlink = [&](int32_t k) {
+        const int32_t p = prev[k], q = next[k];
+        if (p != NIL) next[p] = q; else head = q;
+        if (q != NIL) prev[q] = p; else tail = p;
+    };
+    for (int64_t e = 0; e < n_in; ++e) {
+        const int64_t k = h_in_keys[e];
+        RT_ARG(k >= 0 && k < key_bound && hits[(size_t)k] == 0 && h_in_counts[e] > 0, "initial state");
+        hits[(size_t)k] = h_in_counts[e];
+        push_back((int32_t)k);
+        ++size;
+    }
+    for (int64_t e = 0; e < n; ++e) {
+        const int64_t v = h_values[e];
+        RT_ARG(v >= 0 && v < key_bound, "key out of range");
+        const int32_t k = (int32_t)v;
+        if (hits[k] > 0) {
+            if (tail != k) { unlink(k); push_back(k); }
+            ++hits[k];
+        } else {
+            if (size >= capacity) {
+                const int32_t lru = head;
+                unlink(lru);
+                hits[lru] = 0;
+                --size;
+            }
+            hits[k] = 1;
+            push_back(k);
+            ++size;
+        }
+    }
+    int64_t m = 0;
+    for (int32_t k = head; k != NIL; k = next[k]) { h_out_keys[m] = k; h_out_counts[m] = hits[k]; ++m; }
+    *h_n_out = m;
     return RT_OK;
 }

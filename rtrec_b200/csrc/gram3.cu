@@ -128,7 +128,7 @@ __global__ void chunk_count_kernel(int n_items, const int *__restrict__ orig_of,
 // local row of rank-space row jp in the slab of its owner under block-cyclic ownership
 __host__ __device__ __forceinline__ int blk_local_row(int jp, int blk_parts) { return (((jp >> 6) / blk_parts) << 6) | (jp & 63); }
 
-// MODE (rt_set_option("gram_adapt", m), 0 by default until the variants are measured on the GPU):
+// MODE (rt_set_option("gram_adapt", m); default 2: measured 12.03 -> 9.99 ms at the ML-20M shape, profiles/r3a_kbench_gram.log):
 //   1  the four 32-entry batches of a rater's prefetch / update are guarded by warp-uniform tests on the segment length.
 //      On the synthetic ML-20M shape 48 % of the issued batch slots hold an entry (ranges 1..3: 14-28 %, most segments
 //      there are shorter than 32); with the guards it would be 83 % (CPU count over the real segment lengths, DESIGN.md

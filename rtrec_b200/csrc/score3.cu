@@ -153,10 +153,13 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                   const int *__restrict__ ell_off, const int2 *__restrict__ ell, int n_tiles, int n_items, int j_begin,
                   int j_end, int k, int filter, int mode, int tile, int *__restrict__ out_ids,
                   float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ next_query,
-                  const int *__restrict__ order) {
+                  const int *__restrict__ order, const int *__restrict__ n_active_queries) {
     extern __shared__ __align__(16) float acc[];
     __shared__ Score3Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // sparse mode: queries without a single W entry behind their items were answered by query_work_kernel and sit at the
+    // end of order[]; only the first *n_active_queries are scored here
+    if (n_active_queries) n_query = min(n_query, *n_active_queries);
     for (;;) {
         __syncthreads();
         if (tid == 0) sh.q = atomicAdd(next_query, 1);
@@ -173,11 +176,17 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
             const int t1 = min(t0 + tile, j_end);
             const int width = t1 - t0;
             const bool whole = (t0 == 0 && t1 == n_items);
-            {   // tile starts are 16-byte aligned (tile is a multiple of 32 floats)
+            // the tile is zeroed when the first row with entries in it turns up: in sparse mode a tile nothing was added to
+            // holds no candidate and is skipped without being touched (a W with few columns, or a user whose items have
+            // no neighbours in this item range)
+            bool zeroed = false;
+            auto zero_tile = [&]() {   // tile starts are 16-byte aligned (tile is a multiple of 32 floats)
                 const int w4 = width >> 2;
                 for (int x = tid; x < w4; x += S3_NT) reinterpret_cast<float4 *>(acc)[x] = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int x = (w4 << 2) + tid; x < width; x += S3_NT) acc[x] = 0.0f;
-            }
+                __syncthreads();
+                zeroed = true;
+            };
             // ---------------- accumulate: chunks of the user's row ----------------
             for (int c0 = r0; c0 < r1; c0 += S3_CH) {
                 __syncthreads();  // previous chunk fully applied (and acc zeroed) before st.* is rewritten
@@ -218,6 +227,7 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                     __syncthreads();
                 }
                 const int n = sh.n_rows;
+                if (n > 0 && !zeroed) zero_tile();
                 int s = 0;
                 while (s < n) {   // every branch below is uniform across the CTA (the staged list is shared)
                     if (sh.u.st.b[s] < 0) {
@@ -287,6 +297,10 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
                 }
             }
             __syncthreads();
+            if (!zeroed) {
+                if (mode == RT_TOPK_SPARSE) continue;   // nothing scored in this tile: no candidates (CTA-uniform)
+                zero_tile();
+            }
             if (filter) {
                 int fa = r0, fb = r1;
                 if (!whole) { fa = lower_bound3(ridx, r0, r1, t0); fb = lower_bound3(ridx, r0, r1, t1); }
@@ -323,14 +337,40 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
     }
 }
 
-// sort key of a query: its row length (the scoring work grows with it)
-__global__ void query_len_kernel(const int *__restrict__ rptr, const int *__restrict__ users, int n_query,
-                                 unsigned *__restrict__ keys, int *__restrict__ idx) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// sort key of a query: its scoring work = stored W entries behind the items of its row (one warp per query).  In
+// sparse mode a query with no work has an empty answer (no non-zero score): it is written here and never reaches the
+// scoring kernel (n_active counts the others).
+__global__ void __launch_bounds__(256) query_work_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx,
+                                                         const int *__restrict__ users, int n_query,
+                                                         const int *__restrict__ wrptr, int j_begin, int j_end, int n_items,
+                                                         const int *__restrict__ wridx, int k, int sparse,
+                                                         unsigned *__restrict__ keys, int *__restrict__ idx,
+                                                         int *__restrict__ n_active, int *__restrict__ out_ids,
+                                                         float *__restrict__ out_scores, int *__restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (q >= n_query) return;
     const int u = users[q];
-    keys[q] = (unsigned)(rptr[u + 1] - rptr[u]);
-    idx[q] = q;
+    const bool whole = j_begin == 0 && j_end == n_items;
+    unsigned long long work = 0;
+    for (int p = rptr[u] + lane; p < rptr[u + 1]; p += 32) {
+        const int i = ridx[p];
+        int a = wrptr[i], b = wrptr[i + 1];
+        if (!whole && b > a) { a = lower_bound3(wridx, a, b, j_begin); b = lower_bound3(wridx, a, b, j_end); }
+        work += (unsigned)(b - a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
+    const bool skip = sparse && work == 0;
+    if (skip) {
+        for (int e = lane; e < k; e += 32) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+    }
+    if (lane == 0) {
+        // key: work, +1 for every scored query so that only answered ones carry key 0 (they sort to the end)
+        keys[q] = skip ? 0u : (unsigned)min(work + 1ull, 0xffffffffull);
+        idx[q] = q;
+        if (skip) out_cnt[q] = 0; else atomicAdd(n_active, 1);
+    }
 }
 
 // tile geometry shared by the pack builder and the launcher: two CTAs per SM share the shared memory
@@ -460,22 +500,27 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_query) grid = n_query;
-    const int *d_order = nullptr;
+    const int *d_order = nullptr, *d_n_active = nullptr;
     if (n_query > 4 * grid) {
-        // longest-row-first processing order
+        // heaviest-query-first processing order; in sparse mode queries without work are answered on the spot
         const size_t nq = (size_t)n_query;
         unsigned *keys = (unsigned *)rt::scratch(SCR_SCORE, (4 * nq + 256) * sizeof(int));
         if (!keys) return RT_ERR_CUDA;
         unsigned *keys2 = keys + nq + 32;
         int *idx = (int *)(keys2 + nq + 32), *idx2 = idx + nq + 32;
-        query_len_kernel<<<(n_query + 255) / 256, 256, 0, st>>>(d_rptr, d_users, n_query, keys, idx);
+        int *d_cnt_active = d_next + 8;
+        RT_CUDA(cudaMemsetAsync(d_cnt_active, 0, sizeof(int), st));
+        query_work_kernel<<<(unsigned)(((int64_t)n_query * 32 + 255) / 256), 256, 0, st>>>(
+            d_rptr, d_ridx, d_users, n_query, d_wrptr, j_begin, j_end, n_items, d_wridx, k, mode == RT_TOPK_SPARSE ? 1 : 0, keys, idx,
+            d_cnt_active, d_out_ids, d_out_scores, d_out_cnt);
         RT_CHECK_LAUNCH();
         S3_CUB(cub::DeviceRadixSort::SortPairsDescending(d_tmp__, tmp_bytes__, keys, keys2, idx, idx2, n_query, 0, 32, st));
         d_order = idx2;
+        d_n_active = d_cnt_active;
     }
     recommend3_kernel<<<grid, S3_NT, smem, st>>>(
         d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles,
-        n_items, j_begin, j_end, k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next, d_order);
+        n_items, j_begin, j_end, k, filter_interacted, mode, tile, d_out_ids, d_out_scores, d_out_cnt, d_next, d_order, d_n_active);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

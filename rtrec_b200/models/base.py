@@ -21,6 +21,7 @@ from ..utils.identifiers import Identifier
 from ..utils.interactions import UserItemInteractions
 
 FileLike = Union[BytesIO, Any]
+_INT32_MAX = 2**31 - 1
 
 
 class BaseModel(ABC):
@@ -58,8 +59,9 @@ class BaseModel(ABC):
                 user_id = self.user_ids.identify(user)
                 item_id = self.item_ids.identify(item)
                 tstamp, rating = float(tstamp), float(rating)
-                if user_id < 0 or item_id < 0:
-                    raise ValueError(f"negative id ({user_id}, {item_id})")
+                # the device store indexes with int32: an id outside [0, 2^31) is this event's error, not the batch's
+                if not (0 <= user_id <= _INT32_MAX and 0 <= item_id <= _INT32_MAX):
+                    raise ValueError(f"id outside [0, 2^31): ({user_id}, {item_id})")
             except Exception as e:  # noqa: BLE001 - same breadth as the reference
                 logging.warning(f"Error processing interaction: {e}")
                 continue
@@ -78,10 +80,22 @@ class BaseModel(ABC):
     def add_interaction_arrays(self, users, items, tstamps, ratings, update_interaction: bool = False,
                                record_interactions: bool = False) -> None:
         """Column-oriented ``add_interactions`` (same ids, same store state, same recorded items)."""
-        user_ids = self.user_ids.identify_many(users)
-        item_ids = self.item_ids.identify_many(items)
-        self.interactions.add_interactions_batch(user_ids, item_ids, np.asarray(tstamps, dtype=np.float64),
-                                                 np.asarray(ratings, dtype=np.float64), upsert=update_interaction)
+        try:
+            user_ids = self.user_ids.identify_many(users)
+            item_ids = self.item_ids.identify_many(items)
+            ts = np.asarray(tstamps, dtype=np.float64)
+            rt = np.asarray(ratings, dtype=np.float64)
+            if len(user_ids) and (min(int(user_ids.min()), int(item_ids.min())) < 0
+                                  or max(int(user_ids.max()), int(item_ids.max())) > _INT32_MAX):
+                raise ValueError("ids outside [0, 2^31)")
+        except Exception as e:  # noqa: BLE001
+            # something in the columns is malformed: replay them event by event, so that only the offending events are
+            # skipped with a warning (base.py:85-94) instead of the whole batch raising
+            logging.warning(f"Column ingest fell back to the per-event path: {e}")
+            self.add_interactions(zip(list(users), list(items), list(tstamps), list(ratings)),
+                                  update_interaction=update_interaction, record_interactions=record_interactions)
+            return
+        self.interactions.add_interactions_batch(user_ids, item_ids, ts, rt, upsert=update_interaction)
         if record_interactions:
             self._record_interaction_arrays(user_ids, item_ids)
 
@@ -115,15 +129,15 @@ class BaseModel(ABC):
             item_id = self.item_ids.get_id(item)
             if item_id is None:
                 continue
-            if self.item_ids.pass_through and item_id > self.interactions.max_item_id:
-                continue
+            if self.item_ids.pass_through and not (0 <= item_id <= self.interactions.max_item_id):
+                continue  # unseen (or negative) integer id: not a candidate
             out.append(item_id)
         return out or None
 
     def _resolve_user(self, user: Any) -> Optional[int]:
         uid = self.user_ids.get_id(user)
-        if uid is not None and self.user_ids.pass_through and uid > self.interactions.max_user_id:
-            return None  # unseen integer id: cold start
+        if uid is not None and self.user_ids.pass_through and not (0 <= uid <= self.interactions.max_user_id):
+            return None  # unseen (or negative) integer id: cold start
         return uid
 
     def recommend(self, user: Any, candidate_items: Optional[List[Any]] = None, user_tags: Optional[List[str]] = None,

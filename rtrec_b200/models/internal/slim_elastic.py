@@ -28,6 +28,7 @@ from ..._lib import FitConfig, RT_TOPK_DENSE, RT_TOPK_SPARSE
 
 
 _PINNED: Dict[str, Any] = {}  # pinned host staging buffers for results (grow-only)
+_K_DEVICE = 128               # longest top-k list the fused scoring kernels keep per user (score3.cu KMAX3)
 
 
 def sklearn_seed(random_state) -> int:
@@ -58,6 +59,12 @@ class SLIMElastic:
         # by item column (pipeline.fit_owner_rows) and bulk scoring by query user; every rank ends up with the full W
         # and returns the full result, so the API reads exactly like the single-GPU one.
         self.distributed = bool(config.get("distributed", False))
+        # how bulk scoring sees the query list in SPMD mode: "replicated" = every rank passes the same users, the list is
+        # cut by stored entries, every rank scores its cut and all ranks return all lists (an all-gather); "local" = every
+        # rank passes ITS OWN users (the caller shards the queries, e.g. users[rank::world]) and gets their lists back --
+        # no collective and no foreign Python objects on any rank
+        self.distributed_queries = str(config.get("distributed_queries", "replicated"))
+        assert self.distributed_queries in ("replicated", "local"), self.distributed_queries
         self._W: Optional[D.DeviceW] = None
         self._W_host: Optional[sp.csc_matrix] = None  # lazy mirror / pending upload
         self.last_fit_stats: Optional[np.ndarray] = None
@@ -233,6 +240,18 @@ class SLIMElastic:
                 out.append(items)
         return out
 
+    @staticmethod
+    def _check_user_ids(user_ids: np.ndarray, X: D.DeviceMatrix) -> None:
+        """The kernels index rptr[user] without a bounds test: reject what the reference would reject (scipy row
+        indexing raises IndexError for rows outside the matrix; negative Python indices are not supported here)."""
+        if len(user_ids) and (int(user_ids.min()) < 0 or int(user_ids.max()) >= X.n_users):
+            raise IndexError(f"user id out of range [0, {X.n_users})")
+
+    @staticmethod
+    def _check_item_ids(item_ids: np.ndarray, n_items: int, what: str = "candidate item") -> None:
+        if len(item_ids) and (int(item_ids.min()) < 0 or int(item_ids.max()) >= n_items):
+            raise IndexError(f"{what} id out of range [0, {n_items})")
+
     def recommend_batch_device(self, user_ids: np.ndarray, X: D.DeviceMatrix, candidate_item_ids=None, top_k: int = 10,
                                filter_interacted: bool = True, dense_output: bool = True):
         """Array form: returns host arrays (ids int64 [Q,k] with -1 padding, scores f32 [Q,k], cnt [Q])."""
@@ -241,20 +260,68 @@ class SLIMElastic:
         if X.n_items != n_items:
             # the reference multiplies (n_users x I_x) by (I_w x I_w): shapes must agree
             raise ValueError(f"dimension mismatch: interaction matrix has {X.n_items} items, W has {n_items}")
-        users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
+        user_ids = np.ascontiguousarray(user_ids, dtype=np.int64)
+        self._check_user_ids(user_ids, X)
         k = int(top_k)
         if candidate_item_ids is not None:
-            cand_host = np.ascontiguousarray(candidate_item_ids, dtype=np.int32)
-            cand = D.to_dev(cand_host)
-            kk = max(1, min(k, len(cand_host), 128))
+            cand_host = np.ascontiguousarray(candidate_item_ids, dtype=np.int64)
+            self._check_item_ids(cand_host, n_items)
+            if min(k, len(cand_host)) > _K_DEVICE:
+                return self._topk_large(user_ids, X, k, filter_interacted, dense_output, cand_host)
+            users = D.to_dev(user_ids.astype(np.int32))
+            cand = D.to_dev(cand_host.astype(np.int32))
+            kk = max(1, min(k, len(cand_host)))
             pos, scores, cnt = D.recommend_candidates(X, users, W, cand, kk)
             pos = pos.cpu().numpy().astype(np.int64)
             ids = np.where(pos >= 0, cand_host[np.clip(pos, 0, len(cand_host) - 1)], -1)
             return ids, scores.cpu().numpy(), cnt.cpu().numpy()
-        kk = max(1, min(k, 128))
+        if k > _K_DEVICE:
+            return self._topk_large(user_ids, X, k, filter_interacted, dense_output, None)
+        users = D.to_dev(user_ids.astype(np.int32))
         mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
-        ids, scores, cnt = D.recommend(X, users, W, kk, filter_interacted, mode)
+        ids, scores, cnt = D.recommend(X, users, W, max(1, k), filter_interacted, mode)
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
+
+    def _topk_large(self, user_ids: np.ndarray, X: D.DeviceMatrix, k: int, filter_interacted: bool, dense_output: bool,
+                    cand_host: Optional[np.ndarray]):
+        """top_k > 128 (the fused kernels keep at most 128 entries per user in shared memory): the scores come from the
+        candidate-scoring kernel (every requested column with its float32 score, 128 columns per launch), the selection
+        follows slim_elastic.py:723-818 on those scores: candidates / dense mode ``argsort(scores)[-k:][::-1]`` minus
+        -inf entries, sparse mode = non-zero scores by descending score.  Users are processed in chunks of bounded size."""
+        n_items = X.n_items
+        k_eff = min(k, len(cand_host) if cand_host is not None else n_items)
+        Q = len(user_ids)
+        ids = np.full((Q, k_eff), -1, dtype=np.int64)
+        scores = np.zeros((Q, k_eff), dtype=np.float32)
+        cnt = np.zeros(Q, dtype=np.int32)
+        n_cols = len(cand_host) if cand_host is not None else n_items
+        step = max(1, min(4096, (1 << 26) // max(n_cols, 1)))
+        rptr = ridx = None
+        if filter_interacted and cand_host is None:
+            rptr, ridx = X.rptr.cpu().numpy(), X.ridx[:X.nnz].cpu().numpy()
+        for a in range(0, Q, step):
+            S = self._scores_device(user_ids[a:a + step], X, cand_host, "batch_recommend")
+            for r in range(S.shape[0]):
+                sc = S[r]
+                if cand_host is not None:
+                    top = np.argsort(sc)[-k:][::-1]
+                    out_ids = cand_host[top]
+                else:
+                    if rptr is not None:
+                        u = int(user_ids[a + r])
+                        sc[ridx[rptr[u]:rptr[u + 1]]] = -np.inf
+                    if dense_output:
+                        top = np.argsort(sc)[-k:][::-1]
+                        top = top[sc[top] != -np.inf]
+                    else:
+                        nz = np.flatnonzero((sc != 0) & (sc != -np.inf))
+                        top = nz[np.argsort(-sc[nz], kind="stable")][:k]
+                    out_ids = top
+                c = len(top)
+                ids[a + r, :c] = out_ids
+                scores[a + r, :c] = sc[top]
+                cnt[a + r] = c
+        return ids, scores, cnt
 
     _LIST_CHUNK = 16384  # users per launch when the result is wanted as Python lists
 
@@ -268,11 +335,16 @@ class SLIMElastic:
         if X.n_items != W.n_items:
             raise ValueError(f"dimension mismatch: interaction matrix has {X.n_items} items, W has {W.n_items}")
         Q = len(user_ids)
-        k = max(1, min(int(top_k), 128))
+        user_ids = np.ascontiguousarray(user_ids, dtype=np.int64)
+        self._check_user_ids(user_ids, X)
+        if int(top_k) > _K_DEVICE:
+            ids, _, cnt = self._topk_large(user_ids, X, int(top_k), filter_interacted, dense_output, None)
+            return [row[:c].tolist() for row, c in zip(ids, cnt.tolist())]
+        k = max(1, int(top_k))
         mode = RT_TOPK_DENSE if dense_output else RT_TOPK_SPARSE
-        users = D.to_dev(np.ascontiguousarray(user_ids, dtype=np.int32))
+        users = D.to_dev(user_ids.astype(np.int32))
         ctx = self._dist_ctx()
-        if ctx is not None and Q >= 64 * ctx[1]:
+        if ctx is not None and Q >= 64 * ctx[1] and getattr(self, "distributed_queries", "replicated") != "local":
             # query-sharded scoring: every rank scores its slice of the users, the finished lists are all-gathered
             from ... import pipeline as P
             ids, _, cnt = P.recommend_query_sharded(X, users, W, k, filter_interacted, mode, rank=ctx[0], world=ctx[1])
@@ -331,7 +403,9 @@ class SLIMElastic:
 
     def similar_items_batch(self, item_ids: np.ndarray, top_k: int = 10):
         W = self._require_fitted("similar_items")
-        items = D.to_dev(np.ascontiguousarray(item_ids, dtype=np.int32))
+        item_ids = np.ascontiguousarray(item_ids, dtype=np.int64)
+        self._check_item_ids(item_ids, W.n_items, "query item")   # the reference's W[:, item_id] raises IndexError
+        items = D.to_dev(item_ids.astype(np.int32))
         ids, scores, cnt = D.similar(W, items, max(1, int(top_k)))
         return ids.cpu().numpy().astype(np.int64), scores.cpu().numpy(), cnt.cpu().numpy()
 

@@ -74,6 +74,19 @@ def build_matrix(state: StoreState, *, decay_rate: Optional[float], max_ts: Opti
     return D.DeviceMatrix(n_users, n_items, int(nnz.value), rptr, ridx, rval, cptr, cidx, cval, ccol, bool(nonneg.value))
 
 
+def touched_items(di, dd, n_items: int):
+    """Item bookkeeping of a device-resident event batch (rt_events_item_stats32; base.py:85-94 records the item of
+    every event for the partial fit, slim.py:31-53): returns ``(mask uint8 [n_items] device, targets int32 device)``
+    -- the 0/1 column mask ``build_matrix(item_mask=...)`` takes and the ascending list of touched item ids."""
+    t = D.require_cuda()
+    n = int(di.numel())
+    cnt = D.empty(n_items, t.int32); last = D.empty(n_items, t.int32); seen = D.empty(n_items, t.uint8)
+    _lib.check(_lib.load().rt_events_item_stats32(D.ptr(di), D.ptr(dd), n, int(n_items), D.ptr(cnt), D.ptr(last),
+                                                  D.ptr(seen), D.stream_ptr()), "rt_events_item_stats32")
+    ids = np.flatnonzero(seen.cpu().numpy()).astype(np.int32)   # a few KB; the host keeps this list anyway (slim.py:29)
+    return seen, D.to_dev(ids)
+
+
 # ------------------------------------------------------------------------------------------ sharding
 def item_shard(n_items: int, rank: int, world: int, cptr_host: Optional[np.ndarray] = None) -> Tuple[int, int]:
     """Contiguous item range [j0, j1) owned by ``rank``: equal column counts.  One ElasticNet solve costs
@@ -326,30 +339,44 @@ def all_gather_ragged(x, counts: list, group=None):
 
 def gather_solve_results(res: D.SolveResult, world: int, group=None) -> D.SolveResult:
     """All-gather (NCCL) of the per-rank solver outputs: every rank ends up with the (target, rows, values)
-    triples of all targets, ready for ``w_merge``."""
+    triples of all targets, ready for ``w_merge``.  Two collectives: the (n_targets, n_pairs) header, then ONE packed
+    int32 buffer per rank -- targets | cnt | stats | off (as two int32 halves) | rows | value bits -- instead of one
+    all-gather per array (seven launches and seven padded staging buffers at ~3 MB of payload, SCALE_r01)."""
     if world <= 1:
         return res
     import torch.distributed as dist
     t = D.torch()
     dev = res.targets.device
     T = int(res.targets.numel())
-    meta = t.tensor([T, int(res.n_pairs)], dtype=t.int64, device=dev)
+    P_ = int(res.n_pairs)
+    meta = t.tensor([T, P_], dtype=t.int64, device=dev)
     metas = t.empty((world, 2), dtype=t.int64, device=dev)
     dist.all_gather_into_tensor(metas.view(-1), meta, group=group)
     metas = metas.cpu().tolist()
     Ts = [int(m[0]) for m in metas]
     Ps = [int(m[1]) for m in metas]
-    g_t = all_gather_ragged(res.targets, Ts, group)
-    g_off = all_gather_ragged(res.off, Ts, group)
-    g_cnt = all_gather_ragged(res.cnt, Ts, group)
-    g_rows = all_gather_ragged(res.rows, Ps, group)
-    g_vals = all_gather_ragged(res.vals, Ps, group)
-    g_stats = all_gather_ragged(res.stats.reshape(-1), [4 * x for x in Ts], group)
-    base, off = 0, []
+    Tm, Pm = max(max(Ts), 1), max(max(Ps), 1)
+    width = 8 * Tm + 2 * Pm               # targets, cnt: Tm each; stats: 4 Tm; off: 2 Tm; rows, vals: Pm each
+    buf = t.zeros(width, dtype=t.int32, device=dev)
+    if T:
+        buf[0:T] = res.targets
+        buf[Tm:Tm + T] = res.cnt[:T]
+        buf[2 * Tm:2 * Tm + 4 * T] = res.stats.reshape(-1)[:4 * T]
+        buf[6 * Tm:6 * Tm + 2 * T] = res.off[:T].view(t.int32)
+    if P_:
+        buf[8 * Tm:8 * Tm + P_] = res.rows[:P_]
+        buf[8 * Tm + Pm:8 * Tm + Pm + P_] = res.vals[:P_].view(t.int32)
+    out = t.empty((world, width), dtype=t.int32, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), buf, group=group)
+    g_t, g_cnt, g_stats, g_off, g_rows, g_vals = [], [], [], [], [], []
+    base = 0
     for r in range(world):
-        off.append(g_off[r] + base)
-        base += Ps[r]
-    return D.SolveResult(t.cat(g_t), t.cat(off), t.cat(g_cnt), t.cat(g_rows), t.cat(g_vals), None,
+        o, Tr, Pr = out[r], Ts[r], Ps[r]
+        g_t.append(o[0:Tr]); g_cnt.append(o[Tm:Tm + Tr]); g_stats.append(o[2 * Tm:2 * Tm + 4 * Tr])
+        g_off.append(o[6 * Tm:6 * Tm + 2 * Tr].view(t.int64) + base)
+        g_rows.append(o[8 * Tm:8 * Tm + Pr]); g_vals.append(o[8 * Tm + Pm:8 * Tm + Pm + Pr].view(t.float32))
+        base += Pr
+    return D.SolveResult(t.cat(g_t), t.cat(g_off), t.cat(g_cnt), t.cat(g_rows), t.cat(g_vals), None,
                          t.cat(g_stats).view(-1, 4), res.rows_sorted, base)
 
 

@@ -92,12 +92,32 @@ class Recommender:
 
     def similar_items(self, query_items: List[Any], query_item_tags: Optional[List[str]] = None, top_k: int = 10,
                       ret_scores: bool = False):
+        batch = getattr(self.model, "similar_items_batch", None)
+        if batch is not None and query_item_tags is None and len(query_items) > 1:
+            return batch(query_items, top_k=top_k, ret_scores=ret_scores)   # one launch for the whole list
         return [self.model.similar_items(item, query_item_tags, top_k, ret_scores) for item in query_items]
 
     def evaluate(self, test_data: pd.DataFrame, user_tags: Optional[Dict[Any, List[str]]] = None,
                  recommend_size: int = 10, batch_size=100, filter_interacted: bool = True) -> Dict[str, float]:
-        """recommender.py:163-200.  ``batch_size`` is honoured as a lower bound: the scoring kernel is
+        """recommender.py:163-200.  Models that offer ``evaluate_device`` (SLIM) get the whole evaluation on the device:
+        one scoring launch for all test users and one metrics kernel (``rt_eval_metrics``); the values equal the
+        list-based loop below bit for bit.  Otherwise ``batch_size`` is honoured as a lower bound: the scoring kernel is
         fed at least 16,384 users per launch, which returns the same lists as 100 at a time."""
+        dev = getattr(self.model, "evaluate_device", None)
+        if dev is not None and not user_tags and len(test_data):
+            # device path: ground truth as one flat array grouped by user (same grouping and within-user order as the
+            # groupby below), top-k lists and the nine metrics stay on the device
+            try:
+                import numpy as np
+                codes, uniques = pd.factorize(test_data["user"], sort=True)
+                order = np.argsort(codes, kind="stable")
+                gptr = np.concatenate([[0], np.cumsum(np.bincount(codes, minlength=len(uniques)))])
+                res = dev(uniques.tolist() if uniques.dtype.kind == "O" else np.asarray(uniques), gptr,
+                          test_data["item"].to_numpy()[order], recommend_size, filter_interacted)
+            except TypeError:
+                res = None   # user keys that cannot be ordered: pandas' groupby decides below
+            if res is not None:
+                return res
         grouped = test_data.groupby("user")["item"].apply(list).to_dict()
         users = list(grouped.keys())
         step = max(int(batch_size), _EVAL_DEVICE_BATCH)

@@ -52,7 +52,16 @@ class Identifier:
 
     def identify_many(self, objs) -> np.ndarray:
         """ids of a whole column, in order; equals ``[self.identify(o) for o in objs]``."""
-        arr = np.asarray(objs)
+        if isinstance(objs, np.ndarray):
+            arr = objs
+        else:
+            objs = list(objs)
+            # a list of Python objects keeps its element types (np.asarray would silently turn [1, "a"] into strings and
+            # hide the "Mixed types" error the per-event path raises)
+            arr = np.asarray(objs) if all(_is_int(o) for o in objs[:64]) else np.empty(0, dtype=object)
+            if arr.dtype.kind not in "iu":
+                arr = np.empty(len(objs), dtype=object)
+                arr[:] = objs
         if arr.dtype.kind in "iu" and not self.force_identify:
             if self.pass_through is False:
                 raise self._mixed(arr[0] if len(arr) else None)

@@ -203,7 +203,9 @@ class UserItemInteractions:
         if not self.hot_items.add_counts(hot, cnt_h[hot], last_h[hot]):
             # an LRU eviction can happen inside the batch: replay the hot-item updates event by event on the host
             pos = d > 0
-            self.hot_items.add_batch(i[pos] if not pos.all() else i)
+            vals = i[pos] if not pos.all() else i
+            if not self.hot_items._replay_native(vals):
+                self.hot_items.add_batch(vals)
         self.all_item_ids.update(np.flatnonzero(seen_h).tolist())
         return self._queue_device_batch(du, di, dts, dd, upsert, int(hi_u.value), imax, float(mx_ts.value), None, None)
 
@@ -389,7 +391,13 @@ class UserItemInteractions:
         return items.tolist()
 
     def _n_users_seen(self) -> int:
-        return len(self.get_all_users())
+        """Distinct users in the store (cached per store version: ``get_user_items(n_recent=...)`` asks per lookup)."""
+        hit = getattr(self, "_n_users_cache", None)
+        if hit is not None and hit[0] == self.version:
+            return hit[1]
+        n = len(self.get_all_users())
+        self._n_users_cache = (self.version, n)
+        return n
 
     def get_all_item_ids(self) -> List[int]:
         return list(self.all_item_ids)

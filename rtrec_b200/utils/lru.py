@@ -70,8 +70,38 @@ class LRUFreqSet(MutableSet):
             last[inv] = np.arange(n)  # later occurrences overwrite earlier ones
         if not self.add_counts(uniq, counts, last):
             # an eviction can happen somewhere inside the batch: replay it event by event
-            for v in values.tolist():
-                self.add(v)
+            if not self._replay_native(values):
+                for v in values.tolist():
+                    self.add(v)
+
+    def _replay_native(self, values: np.ndarray) -> bool:
+        """Event-by-event replay in the library's host code (``rt_lru_replay``) for non-negative integer keys; False when
+        the keys do not qualify (the caller then runs the Python loop)."""
+        if values.dtype.kind not in "iu" or len(values) < 4096:
+            return False
+        try:
+            import ctypes as C
+            from .. import _lib
+            lib = _lib.load()
+            cur_k = np.fromiter(self.data.keys(), dtype=np.int64, count=len(self.data))
+            cur_c = np.fromiter(self.data.values(), dtype=np.int64, count=len(self.data))
+        except Exception:  # noqa: BLE001 - library not built, or non-integer keys in the set
+            return False
+        lo = min(int(values.min()), int(cur_k.min()) if len(cur_k) else 0)
+        bound = max(int(values.max()), int(cur_k.max()) if len(cur_k) else 0) + 1
+        if lo < 0 or bound > (1 << 28):
+            return False
+        vals = np.ascontiguousarray(values, dtype=np.int64)
+        out_k = np.empty(self.capacity, dtype=np.int64)
+        out_c = np.empty(self.capacity, dtype=np.int64)
+        n_out = C.c_int64(0)
+        rc = lib.rt_lru_replay(vals.ctypes.data, len(vals), self.capacity, bound, cur_k.ctypes.data, cur_c.ctypes.data, len(cur_k),
+                               out_k.ctypes.data, out_c.ctypes.data, C.byref(n_out))
+        if rc != 0:
+            return False
+        m = int(n_out.value)
+        self.data = OrderedDict(zip(out_k[:m].tolist(), out_c[:m].tolist()))
+        return True
 
     def add_counts(self, uniq: np.ndarray, counts: np.ndarray, last: np.ndarray) -> bool:
         """Apply a batch summarised as (distinct key, number of adds, arrival index of its last add).

@@ -16,8 +16,8 @@ SHAPES = {
 }
 
 
-def synth_events(n_users, n_items, n_events, seed=0, rating="int", dup_frac=0.0, span_days=365.0, cap=0.5):
-    rng = np.random.default_rng(seed)
+def synth_probs(rng, n_users, n_items, n_events, cap=0.5):
+    """(p_user, p_item) of the recipe above; consumes exactly one lognormal draw of ``rng``."""
     p_item = (np.arange(n_items) + 1.0) ** -0.9
     p_item /= p_item.sum()
     p_user = rng.lognormal(0, 1, n_users)
@@ -30,6 +30,12 @@ def synth_events(n_users, n_items, n_events, seed=0, rating="int", dup_frac=0.0,
             break
         p_item[over] = lim
         p_item /= p_item.sum()
+    return p_user, p_item
+
+
+def synth_events(n_users, n_items, n_events, seed=0, rating="int", dup_frac=0.0, span_days=365.0, cap=0.5):
+    rng = np.random.default_rng(seed)
+    p_user, p_item = synth_probs(rng, n_users, n_items, n_events, cap)
     n_unique = int(round(n_events * (1.0 - dup_frac)))
     u_parts, i_parts, have = [], [], 0
     seen = None
@@ -73,3 +79,36 @@ def synth_shape(name: str, scale: float = 1.0, **over):
     kw = dict(seed=seed, rating=kind, span_days=span, dup_frac=0.15 if name == "hm" else 0.0)
     kw.update(over)
     return synth_events(U, I, N, **kw)
+
+
+def synth_stream(name: str, base_u, base_i, n_batches: int, batch_events: int, seed: int = 3, frac_existing: float = 0.8):
+    """Event batches that FOLLOW the base events ``(base_u, base_i)`` of shape ``name`` in time (SURVEY.md 8d, C4 =
+    BASELINE configs[3], streaming partial fit): ``frac_existing`` of a batch re-rates (user, item) pairs drawn uniformly
+    from the base events, the rest are pairs drawn from the same user-activity / item-popularity laws as the base
+    (mostly new pairs); pairs may repeat inside a batch (``update_interaction=True``: the last event wins); batch b
+    covers day b after the end of the base span, timestamps ascending."""
+    U, I, N, kind, span, base_seed = SHAPES[name]
+    base_u, base_i = np.asarray(base_u), np.asarray(base_i)
+    U, I = int(base_u.max()) + 1, int(base_i.max()) + 1
+    p_user, p_item = synth_probs(np.random.default_rng(base_seed), U, I, len(base_u))
+    t_end = 1.0e9 + span * 86400
+    n_old = int(round(batch_events * frac_existing))
+    out = []
+    for b in range(n_batches):
+        rng = np.random.default_rng(seed + 1000 * b)
+        pick = rng.integers(0, len(base_u), n_old)
+        u = np.concatenate([base_u[pick], rng.choice(U, size=batch_events - n_old, p=p_user)]).astype(np.int64)
+        i = np.concatenate([base_i[pick], rng.choice(I, size=batch_events - n_old, p=p_item)]).astype(np.int64)
+        perm = rng.permutation(batch_events)
+        u, i = u[perm], i[perm]
+        ts = t_end + b * 86400 + np.sort(rng.integers(0, 86400, batch_events)).astype(np.float64)
+        if kind == "half":
+            r = rng.integers(1, 11, batch_events).astype(np.float64) * 0.5
+        elif kind == "int":
+            r = rng.integers(1, 6, batch_events).astype(np.float64)
+        elif kind == "one":
+            r = np.ones(batch_events)
+        else:
+            r = rng.uniform(0.5, 5.0, batch_events)
+        out.append((u, i, ts, r))
+    return out

@@ -8,7 +8,7 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from oracle.synth import synth_events
+from rtrec_b200.utils.synth import synth_events
 
 pytestmark = pytest.mark.gpu
 
@@ -226,3 +226,100 @@ def test_recommend_lists_chunked_pipeline_equals_single_launch(golden):
         assert got == want
     ids, _, cnt = m.model.recommend_batch_device(np.arange(50), X, None, 10, True, False)
     assert m.recommend_batch(list(range(50)), top_k=10) == [row[:c] for row, c in zip(ids.tolist(), cnt.tolist())]
+
+
+# ------------------------------------------------------------------------------------------ round-2 API hardening
+def _small_model(ids_kind="int", nn=20):
+    from rtrec_b200.models import SLIM
+    u, i, ts, r = synth_events(500, 400, 20000, seed=31, rating="cont")
+    m = SLIM(nn_feature_selection=nn)
+    if ids_kind == "int":
+        m.add_interaction_arrays(u, i, ts, r)
+    else:
+        m.add_interaction_arrays(np.asarray([f"u{x}" for x in u], dtype=object), np.asarray([f"i{x}" for x in i], dtype=object), ts, r)
+    m.bulk_fit()
+    return m, u, i
+
+
+@pytest.mark.parametrize("dense_output", [True, False])
+def test_top_k_above_128_is_not_truncated(dense_output):
+    """top_k > 128: the reference returns up to top_k items; the fused kernels keep 128 per user, so longer
+    lists come from the candidate-scoring kernel + the reference's selection rule.  The first 128 entries must equal the
+    fused kernel's list wherever scores are untied, and the whole list must be a valid top-k of X @ W."""
+    import scipy.sparse as sp
+    from tests.helpers import topk_consistent
+    m, u, i = _small_model()
+    X = m.interactions.to_csr()
+    W = m.model.item_similarity.tocsc().astype(np.float32)
+    users = np.arange(0, 60)
+    k = 200
+    out = m.model.recommend_batch(users.tolist(), X, top_k=k, filter_interacted=True, dense_output=dense_output, ret_scores=True)
+    S = np.asarray((X[users, :] @ W).todense(), dtype=np.float32)
+    n_items = X.shape[1]
+    for q, (items, scores) in enumerate(out):
+        inter = np.zeros(n_items, bool)
+        inter[X[int(users[q])].indices] = True
+        elig = ~inter if dense_output else (~inter & (S[q] != 0))
+        assert len(items) == min(k, int(elig.sum())), (q, len(items))
+        ok, why = topk_consistent(items, S[q], k, elig, tol=2e-5)
+        assert ok, (q, why)
+    # candidates: more than 128 candidates and k > 128 -> every candidate comes back, ordered by score
+    cand = list(range(0, 300))
+    res = m.model.recommend_batch([3, 4], X, candidate_item_ids=cand, top_k=250)
+    assert all(len(x) == 250 for x in res)
+    # through the model API as well
+    lists = m.recommend_batch([1, 2, 3], top_k=150)
+    assert all(len(set(x)) == len(x) for x in lists) and max(len(x) for x in lists) > 128
+
+
+def test_out_of_range_ids_raise_instead_of_reading_out_of_bounds():
+    """user ids / candidate ids reach kernels that index without bounds tests; the operator rejects them like
+    scipy indexing does (IndexError), the model treats unseen or negative pass-through ids as cold users / non-candidates."""
+    m, u, i = _small_model()
+    X = m.interactions.to_csr()
+    n_users, n_items = X.shape
+    for bad in ([n_users], [-1], [0, n_users + 7]):
+        with pytest.raises(IndexError):
+            m.model.recommend_batch(bad, X, top_k=5)
+    with pytest.raises(IndexError):
+        m.model.recommend_batch([0], X, candidate_item_ids=[1, n_items], top_k=5)
+    with pytest.raises(IndexError):
+        m.model.recommend_batch([0], X, candidate_item_ids=[-5, 1], top_k=5)
+    with pytest.raises(IndexError):
+        m.model.similar_items(n_items + 3)
+    hot = m.interactions.get_hot_items(5, filter_interacted=False)
+    assert m.recommend(-1, top_k=5) == hot                       # negative pass-through id = unknown user
+    assert m.recommend_batch([-3, n_users + 10], top_k=5) == [hot, hot]
+    got = m.recommend(0, candidate_items=[-5, 1, 2, n_items + 100], top_k=5)
+    assert set(got) <= {1, 2}
+
+
+def test_bad_events_are_skipped_one_by_one(caplog):
+    """base.py:85-94: only the malformed event is dropped (an id >= 2^31 used to drop the whole call)."""
+    from rtrec_b200.models import SLIM
+    m = SLIM()
+    ev = [(1, 2, 1.0e9, 3.0), (2**31 + 5, 3, 1.0e9, 1.0), (4, "x", 1.0e9, 1.0), (5, 6, "bad", 1.0), (7, 8, 1.0e9 + 1, 2.0)]
+    m.add_interactions(ev)
+    X = m.interactions.to_csr()
+    assert X.nnz == 2 and X[1, 2] == 3.0 and X[7, 8] == 2.0
+    # the column path falls back to the per-event path when a column is malformed
+    m2 = SLIM()
+    m2.add_interaction_arrays([1, 2**31 + 5, 7], [2, 3, 8], [1.0e9, 1.0e9, 1.0e9 + 1], [3.0, 1.0, 2.0])
+    X2 = m2.interactions.to_csr()
+    assert X2.nnz == 2 and X2[1, 2] == 3.0 and X2[7, 8] == 2.0
+    m3 = SLIM()
+    m3.add_interaction_arrays([1, "a", 7], [2, 3, 8], [1.0e9, 1.0e9, 1.0e9 + 1], [3.0, 1.0, 2.0])   # mixed id kinds
+    assert m3.interactions.to_csr().nnz == 2
+
+
+@pytest.mark.parametrize("ids_kind", ["int", "str"])
+def test_similar_items_batch_equals_one_by_one(ids_kind):
+    from rtrec_b200.recommender import Recommender
+    m, u, i = _small_model(ids_kind)
+    rec = Recommender(m)
+    q = list(range(0, 120)) if ids_kind == "int" else [f"i{x}" for x in range(0, 120)]
+    for ret_scores in (False, True):
+        got = rec.similar_items(q, top_k=7, ret_scores=ret_scores)
+        want = [m.similar_items(x, None, 7, ret_scores) for x in q]
+        assert got == want
+    assert any(len(x) for x in got)

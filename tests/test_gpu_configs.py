@@ -13,7 +13,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import slim_oracle as so
-from oracle.synth import synth_events
+from rtrec_b200.utils.synth import synth_events
 from tests.helpers import assert_w_parity, topk_consistent
 
 pytestmark = pytest.mark.gpu

@@ -1,28 +1,96 @@
-"""BASELINE.json configs[1] at its FULL size (synthetic MovieLens-20M shape: 138,493 x 26,744, 20M ratings,
-nn_feature_selection=50) on the GPU, through the public API: size-independent properties of every stage plus
-oracle parity on a sample of columns and users (the oracle needs ~40 ms per column at this size, so the whole
-fit cannot be replayed on the CPU inside a test).
+"""BASELINE.json configs[1], [2] and [3] at their FULL sizes on the GPU, through the public API: size-independent
+properties of every stage plus oracle parity on stratified samples of columns and users (the oracle needs tens of
+milliseconds per column at these sizes, so a whole fit cannot be replayed on the CPU inside a test).
 
+configs[1]  synthetic MovieLens-20M shape, 138,493 x 26,744, 20M ratings, nn_feature_selection=50
   store    CSR and CSC hold the same 20M entries, canonical (sorted, no duplicates), bit-equal to the folded events
   fit      W >= 0, zero diagonal, <= nn entries per column, every entry's row is a co-rated item;
-           sampled columns within the at-scale parity bar of tests/helpers.py against the oracle (same candidates):
-           1e-4 of the column maximum wherever that maximum is >= 1e-3, absolute 1e-5 + equal ElasticNet objectives
-           where the reference's own float32 noise exceeds 1e-4 of a tiny column (tests/c2_parity_cpu.py)
+           >= 256 sampled columns, stratified by popularity decile and by "the device solution is not all zero", within
+           the at-scale parity bar of tests/helpers.py against the oracle (same candidates): 1e-4 of the column maximum
+           wherever that maximum is >= 1e-3, absolute 1e-5 + equal ElasticNet objectives where the reference's own float32
+           noise exceeds 1e-4 of a tiny column (tests/c2_parity_cpu.py)
   scoring  every list: <= 10 items, no interacted item, no duplicates, scores descending and > 0 (int ids -> sparse
-           semantics); sampled users: valid top-10 of the oracle's scores; an order-independent checksum of all lists
-           is reproduced by a second pass in one launch instead of chunks
+           semantics); 1,000 sampled users: valid top-10 of the oracle's scores; the chunked list pipeline equals one launch
+configs[3]  the same model, then ``Recommender.fit(batch, update_interaction=True)`` with a 1M-event batch (80 % re-rated
+           pairs) and a 50k-event batch confined to part of the catalogue: store bit-equal to the oracle's fold, columns of
+           untouched items bit-identical to before, sampled re-solved columns against the oracle on the masked matrix
+configs[2]  synthetic H&M shape, 1,371,980 x 105,542, 31M events with repeats, SLIM(decay_in_days=180), all features, and
+           the nn_feature_selection=50 variant of the reference notebook: store against the oracle's fold (accumulate +
+           clip + decay), EVERY column that can be non-zero (Cauchy-Schwarz bound on the Gram row) against the oracle,
+           no other column non-zero, sampled users
 """
 import numpy as np
+import pandas as pd
 import pytest
 import scipy.sparse as sp
 
 from oracle import slim_oracle as so
-from oracle.synth import synth_shape
-from tests.helpers import assert_w_parity_at_scale, topk_consistent
+from rtrec_b200.utils.synth import synth_shape, synth_stream
+from tests.helpers import assert_w_parity_at_scale, column_errors, topk_consistent
 
 pytestmark = pytest.mark.gpu
+N_THREADS = 16
 
 
+def oracle_columns(Xc, cols, nn, sel=None):
+    res, _, _ = so.fit_columns(Xc, np.asarray(cols, dtype=np.int32), nn, sel_in=sel, n_threads=N_THREADS)
+    colsd = {}
+    for j, (rows, vals) in zip(cols, res):
+        so.SlimOracle._apply(colsd, int(j), rows, vals)
+    return so.SlimOracle._to_csc(colsd, Xc.shape[1])
+
+
+def stratified_columns(W, Xc, rng, per_decile_nontrivial=16, per_decile_any=10, among=None):
+    """columns by popularity decile (stored entries of the column): some whose device solution is not all zero, some at random"""
+    I = Xc.shape[1]
+    pool = np.arange(I) if among is None else np.asarray(among)
+    cl = np.diff(Xc.indptr)[pool]
+    order = pool[np.argsort(-cl, kind="stable")]
+    nz = np.diff(W.indptr) > 0
+    picks = []
+    for d in range(10):
+        dec = order[len(order) * d // 10: len(order) * (d + 1) // 10]
+        nt = dec[nz[dec]]
+        if len(nt):
+            picks.append(rng.choice(nt, min(per_decile_nontrivial, len(nt)), replace=False))
+        picks.append(rng.choice(dec, min(per_decile_any, len(dec)), replace=False))
+    return np.unique(np.concatenate(picks)).astype(np.int32)
+
+
+def device_sel(m, cols):
+    pos = {int(t): k for k, t in enumerate(m.model.last_fit_targets)}
+    return np.stack([m.model.last_fit_sel[pos[int(j)]] for j in cols])
+
+
+def check_lists(lists, u, i, U, I):
+    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=U)
+    assert lens.max() <= 10
+    flat = np.fromiter((y for x in lists for y in x), dtype=np.int64, count=int(lens.sum()))
+    if len(flat):
+        assert flat.min() >= 0 and flat.max() < I
+    owner = np.repeat(np.arange(U, dtype=np.int64), lens)
+    key = owner * I + flat
+    assert len(np.unique(key)) == len(key)                                   # no duplicates inside a list
+    seen = np.unique(u.astype(np.int64) * I + i)
+    assert not np.isin(key, seen).any()                                      # interacted items are filtered
+    return lens, flat
+
+
+def check_sampled_users(m, lists, users, tol=2e-5):
+    W = m.model.item_similarity.tocsc().astype(np.float32)
+    Xr = m.interactions.to_csr()
+    I = Xr.shape[1]
+    for a in range(0, len(users), 250):
+        chunk = users[a:a + 250]
+        S = np.asarray((Xr[chunk, :] @ W).todense(), dtype=np.float32)
+        for q, uid in enumerate(chunk):
+            inter = np.zeros(I, bool)
+            inter[Xr[uid].indices] = True
+            ok, why = topk_consistent(lists[uid], S[q], 10, ~inter & (S[q] != 0), tol=tol)
+            assert ok, (int(uid), why)
+
+
+# ================================================================================================== configs[1]
 @pytest.fixture(scope="module")
 def c2():
     from rtrec_b200.models import SLIM
@@ -57,24 +125,17 @@ def test_c2_fit_full_size(c2):
     assert (W.data > 0).all() and (W.diagonal() == 0).all()
     assert np.diff(W.indptr).max() <= 50
     Xc = m.interactions.to_csc()
-    rng = np.random.default_rng(7)
-    nz_cols = np.flatnonzero(np.diff(W.indptr) > 0)
-    cols = np.sort(np.concatenate([rng.choice(nz_cols, 12, replace=False), rng.choice(I, 12, replace=False)])).astype(np.int32)
-    cols = np.unique(cols)
+    cols = stratified_columns(W, Xc, np.random.default_rng(7))
+    assert len(cols) >= 256 and int((np.diff(W.indptr)[cols] > 0).sum()) >= 128, (len(cols), int((np.diff(W.indptr)[cols] > 0).sum()))
     # same candidate order as the device chose (exact integer-rating ties at the cut, SURVEY.md hard part 3)
-    tg = m.model.last_fit_targets
-    pos = {int(t): k for k, t in enumerate(tg)}
-    sel = np.stack([m.model.last_fit_sel[pos[int(j)]] for j in cols])
-    res, _, _ = so.fit_columns(Xc, cols, 50, sel_in=sel, n_threads=8)
-    o = so.SlimOracle({"nn_feature_selection": 50})
-    colsd = {}
-    for j, (rows, vals) in zip(cols, res):
-        so.SlimOracle._apply(colsd, int(j), rows, vals)
-    Wo = so.SlimOracle._to_csc(colsd, I)
-    assert_w_parity_at_scale(W, Wo, cols, Xc, what="W at ML-20M shape")
-    # every neighbour is co-rated with its target (its Gram entry is positive): check on the sampled columns
+    Wo = oracle_columns(Xc, cols, 50, sel=device_sel(m, cols))
+    rel, report = assert_w_parity_at_scale(W, Wo, cols, Xc, what="W at ML-20M shape")
+    r_ = rel[cols]
+    print(f"\n[c2] {len(cols)} columns ({int((np.diff(W.indptr)[cols] > 0).sum())} non-trivial): within 1e-4: {(r_ <= 1e-4).mean():.4f}, "
+          f"1e-4..1e-3: {((r_ > 1e-4) & (r_ <= 1e-3)).mean():.4f}, above: {(r_ > 1e-3).mean():.4f}, worst {r_.max():.3e}")
+    # every neighbour is co-rated with its target (its Gram entry is positive): check on some of the sampled columns
     Xb = (Xc != 0).astype(np.float32)
-    for j in cols:
+    for j in cols[::8]:
         rows = W.indices[W.indptr[j]:W.indptr[j + 1]]
         if len(rows):
             co = np.asarray((Xb[:, rows].T @ Xb[:, [int(j)]]).todense()).ravel()
@@ -86,15 +147,7 @@ def test_c2_scoring_full_size(c2):
     U, I = int(u.max()) + 1, int(i.max()) + 1
     lists = m.recommend_batch(list(range(U)), top_k=10)
     assert len(lists) == U
-    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=U)
-    assert lens.max() <= 10
-    flat = np.fromiter((y for x in lists for y in x), dtype=np.int64, count=int(lens.sum()))
-    assert flat.min() >= 0 and flat.max() < I
-    owner = np.repeat(np.arange(U, dtype=np.int64), lens)
-    key = owner * I + flat
-    assert len(np.unique(key)) == len(key)                                   # no duplicates inside a list
-    seen = np.sort(u.astype(np.int64) * I + i)
-    assert not np.isin(key, seen, assume_unique=False).any()                 # interacted items are filtered
+    lens, flat = check_lists(lists, u, i, U, I)
     # one launch over all users (device arrays) reproduces the chunked list pipeline
     X = m.interactions.device_matrix()
     ids, scores, cnt = m.model.recommend_batch_device(np.arange(U), X, None, 10, True, False)
@@ -105,13 +158,134 @@ def test_c2_scoring_full_size(c2):
     assert ((scores[:, 1:] - scores[:, :-1])[pair] <= 0).all()                # descending inside every list
     assert (scores[valid] > 0).all()                                         # sparse semantics: only scored items
     # sampled users against scores computed on the CPU from the fitted W
-    W = m.model.item_similarity.tocsc().astype(np.float32)
-    Xr = m.interactions.to_csr()
-    rng = np.random.default_rng(11)
-    users = np.sort(rng.choice(U, 96, replace=False))
-    S = np.asarray((Xr[users, :] @ W).todense(), dtype=np.float32)
-    for q, uid in enumerate(users):
-        inter = np.zeros(I, bool)
-        inter[Xr[uid].indices] = True
-        ok, why = topk_consistent(lists[uid], S[q], 10, ~inter & (S[q] != 0), tol=2e-5)
-        assert ok, (int(uid), why)
+    users = np.sort(np.random.default_rng(11).choice(U, 1000, replace=False))
+    check_sampled_users(m, lists, users)
+
+
+# ================================================================================================== configs[3]
+def test_c4_streaming_partial_fit_full_size(c2):
+    """1M-event update_interaction=True batch into the 20M model, then a 50k-event batch confined to 3,000 items."""
+    from rtrec_b200.recommender import Recommender
+    m, u, i, ts, r = c2
+    U, I = int(u.max()) + 1, int(i.max()) + 1
+    rec = Recommender(m)
+    state = so.fold_events(u, i, ts, r)
+    bu, bi, bt, br = synth_stream("ml20m", u, i, 1, 1_000_000)[0]
+    rng = np.random.default_rng(5)
+    sub = np.sort(rng.choice(I, 3000, replace=False))
+    pick = rng.integers(0, len(u), 400_000)
+    pick = pick[np.isin(i[pick], sub)][:50_000]
+    small = (u[pick], i[pick], bt[-1] + 1.0 + np.arange(len(pick), dtype=np.float64), rng.integers(1, 11, len(pick)) * 0.5)
+    for name, (eu, ei, et, er) in (("1M", (bu, bi, bt, br)), ("50k", small)):
+        W_before = m.model.item_similarity.tocsc().copy()
+        rec.fit(pd.DataFrame({"user": eu, "item": ei, "tstamp": et, "rating": er}), update_interaction=True, parallel=True)
+        # ---- store: bit-equal to the oracle's fold with upsert
+        state = so.fold_events(eu, ei, et, er, upsert=True, state=state)
+        Xo = so.state_to_matrix(state, fmt="csc")
+        Xc = m.interactions.to_csc()
+        assert np.array_equal(Xc.indptr, Xo.indptr) and np.array_equal(Xc.indices, Xo.indices) and np.array_equal(Xc.data, Xo.data), name
+        # ---- untouched columns are bit-identical
+        W = m.model.item_similarity.tocsc()
+        touched = np.unique(ei)
+        stale = np.setdiff1d(np.arange(I), touched)
+        for j in stale[:: max(1, len(stale) // 4000)]:
+            a0, a1, b0, b1 = W.indptr[j], W.indptr[j + 1], W_before.indptr[j], W_before.indptr[j + 1]
+            assert np.array_equal(W.indices[a0:a1], W_before.indices[b0:b1]) and np.array_equal(W.data[a0:a1], W_before.data[b0:b1]), (name, int(j))
+        if name == "50k":
+            assert len(stale) > 20_000
+        # ---- re-solved columns against the oracle on the matrix that holds only the touched columns (slim.py:48-53)
+        Xm = so.state_to_matrix(state, fmt="csc", select_items=touched.tolist())
+        assert sorted(int(t) for t in m.model.last_fit_targets) == touched.tolist()
+        cols = stratified_columns(W, Xm, rng, per_decile_nontrivial=8, per_decile_any=4, among=touched)
+        Wo = oracle_columns(Xm, cols, 50, sel=device_sel(m, cols))
+        # the reference's merge keeps old entries of a re-solved column that the new solve does not return (slim_elastic.py
+        # :533-538 assigns only the returned candidates): compare on the candidates of the new solve
+        sel = device_sel(m, cols)
+        Wn = sp.lil_matrix((I, I), dtype=np.float32)
+        for t_, j in enumerate(cols):
+            rows = sel[t_][sel[t_] >= 0]
+            Wn[rows, int(j)] = W[rows, int(j)].toarray().ravel()
+        rel, _ = assert_w_parity_at_scale(Wn.tocsc(), Wo, cols, Xm, what=f"re-solved columns after the {name} batch")
+        print(f"\n[c4 {name}] touched {len(touched)}, stale {len(stale)}, {len(cols)} columns compared, worst {rel[cols].max():.3e}")
+    # ---- re-score
+    lists = m.recommend_batch(list(range(U)), top_k=10)
+    keys = np.asarray(so.state_to_matrix(state, fmt="csr").nonzero())
+    check_lists(lists, keys[0], keys[1], U, I)
+    check_sampled_users(m, lists, np.sort(rng.choice(U, 300, replace=False)))
+
+
+# ================================================================================================== configs[2]
+@pytest.fixture(scope="module")
+def hm_events():
+    return synth_shape("hm")
+
+
+@pytest.fixture(scope="module")
+def hm_oracle_matrix(hm_events):
+    u, i, ts, r = hm_events
+    st = so.fold_events(u, i, ts, r, decay_in_days=180)
+    return st, so.state_to_matrix(st, decay_in_days=180, fmt="csc")
+
+
+def cauchy_schwarz_candidates(Xc, a):
+    """columns whose Gram row CAN hold an entry > a: G[j][c] <= sqrt(G[j][j] G[c][c])"""
+    d = np.asarray(Xc.multiply(Xc).sum(axis=0)).ravel().astype(np.float64)
+    top2 = np.sort(d)[-2:]
+    other = np.where(d == top2[1], top2[0], top2[1])
+    return np.flatnonzero(d * other >= a * a * (1 - 1e-3))
+
+
+def test_c3_hm_all_features_full_size(hm_events, hm_oracle_matrix):
+    from rtrec_b200.models import SLIM
+    u, i, ts, r = hm_events
+    st, Xo = hm_oracle_matrix
+    U, I = int(u.max()) + 1, int(i.max()) + 1
+    m = SLIM(decay_in_days=180)
+    m.add_interaction_arrays(u, i, ts, r)
+    m.bulk_fit()
+    # ---- store: repeated events accumulate and clip, decay at max_timestamp; float32 matrix bit-equal to the oracle's
+    Xc = m.interactions.to_csc()
+    assert Xc.shape == (U, I) and Xc.has_canonical_format
+    assert np.array_equal(Xc.indptr, Xo.indptr) and np.array_equal(Xc.indices, Xo.indices)
+    assert np.array_equal(Xc.data, Xo.data)
+    # ---- W: only columns with a live coordinate can be non-zero; every such column against the oracle
+    W = m.model.item_similarity.tocsc()
+    a = 0.1 * 0.1 * U
+    cand = cauchy_schwarz_candidates(Xo, a)
+    nz_cols = np.flatnonzero(np.diff(W.indptr) > 0)
+    assert np.isin(nz_cols, cand).all(), "a column outside the Cauchy-Schwarz bound is non-zero"
+    assert (W.data > 0).all() and (W.diagonal() == 0).all()
+    rng = np.random.default_rng(3)
+    cols = np.unique(np.concatenate([cand, rng.choice(I, 64, replace=False)])).astype(np.int32)
+    Wo = oracle_columns(Xo, cols, None)
+    assert np.array_equal(np.flatnonzero(np.diff(Wo.indptr) > 0), nz_cols), "non-zero columns differ from the oracle's"
+    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, all features")
+    print(f"\n[c3 all] {len(cand)} candidate columns, {len(nz_cols)} non-zero, nnz(W) = {W.nnz}, worst column error {rel[cols].max():.3e}")
+    # ---- scoring for every user
+    lists = m.recommend_batch(list(range(U)), top_k=10)
+    keys = np.asarray(Xo.nonzero())
+    lens, _ = check_lists(lists, keys[0], keys[1], U, I)
+    assert lens.sum() > 0
+    users = np.unique(np.concatenate([np.flatnonzero(lens > 0)[:500], rng.choice(U, 500, replace=False)]))
+    check_sampled_users(m, lists, users)
+
+
+def test_c3_hm_nn50_full_size(hm_events, hm_oracle_matrix):
+    from rtrec_b200.models import SLIM
+    u, i, ts, r = hm_events
+    st, Xo = hm_oracle_matrix
+    U, I = int(u.max()) + 1, int(i.max()) + 1
+    m = SLIM(decay_in_days=180, nn_feature_selection=50, keep_fit_details=True)
+    m.add_interaction_arrays(u, i, ts, r)
+    m.bulk_fit()
+    W = m.model.item_similarity.tocsc()
+    assert (W.data > 0).all() and (W.diagonal() == 0).all() and np.diff(W.indptr).max() <= 50
+    rng = np.random.default_rng(4)
+    cols = stratified_columns(W, Xo, rng, per_decile_nontrivial=12, per_decile_any=4)
+    Wo = oracle_columns(Xo, cols, 50, sel=device_sel(m, cols))
+    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, nn=50")
+    print(f"\n[c3 nn50] nnz(W) = {W.nnz}, {len(cols)} columns compared ({int((np.diff(W.indptr)[cols] > 0).sum())} non-trivial), worst {rel[cols].max():.3e}")
+    lists = m.recommend_batch(list(range(U)), top_k=10)
+    keys = np.asarray(Xo.nonzero())
+    lens, _ = check_lists(lists, keys[0], keys[1], U, I)
+    check_sampled_users(m, lists, np.sort(rng.choice(U, 500, replace=False)))

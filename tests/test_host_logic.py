@@ -167,3 +167,23 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and "sample" in cb and cb["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert set(line["config"]) >= {"workload", "n_users", "n_items", "n_events"} and "model" not in line["config"]
+
+
+def test_lru_native_replay_equals_python_loop():
+    """rt_lru_replay (host code of the library) == LRUFreqSet.add per event, with evictions inside the batch
+    (/root/reference/rtrec/utils/lru.py:33-47)."""
+    import numpy as np
+    from rtrec_b200.utils.lru import LRUFreqSet
+    rng = np.random.default_rng(0)
+    vals = rng.zipf(1.3, 60000) % 3000
+    a, b = LRUFreqSet(700), LRUFreqSet(700)
+    for v in vals[:5000].tolist():
+        a.add(v); b.add(v)
+    assert a._replay_native(vals[5000:])
+    for v in vals[5000:].tolist():
+        b.add(v)
+    assert list(a.data.items()) == list(b.data.items())
+    assert list(a.get_freq_items(20)) == list(b.get_freq_items(20))
+    c = LRUFreqSet(10)
+    c.add("x")
+    assert not c._replay_native(np.arange(5000))      # non-integer key in the set: the Python loop handles it

@@ -14,7 +14,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import slim_oracle as so
-from oracle.synth import synth_events
+from rtrec_b200.utils.synth import synth_events
 from tests.helpers import assert_w_parity, csc_from, w_from
 
 CASES = [
@@ -133,7 +133,7 @@ def test_gram_form_model_all_columns_ml1m_shape():
     oracle/gram_model.c) against the exact port of the reference path (float32 residual form) on ALL 3,706 columns of the
     synthetic ML-1M-shaped matrix, same candidates -- the parity bar of tests/helpers.py (1e-4 of the column maximum, at
     most 2 % one-sweep flips agreeing to 1e-3 or in objective).  Observed: 7 columns above 1e-4, worst 5.4e-4."""
-    from oracle.synth import synth_shape
+    from rtrec_b200.utils.synth import synth_shape
     from tests.helpers import assert_w_parity_at_scale
     u, i, ts, r = synth_shape("ml1m")
     U, I = int(u.max()) + 1, int(i.max()) + 1

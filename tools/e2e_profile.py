@@ -8,7 +8,7 @@ from rtrec_b200.models import SLIM
 from rtrec_b200.recommender import Recommender
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "ml20m"
-shape, kwargs, desc = bench.WORKLOADS[wl]
+shape, kwargs, desc = (bench.WORKLOADS[wl][k] for k in ("shape", "kwargs", "desc"))
 u, i, ts, r = bench.load_events(shape)
 U = int(u.max()) + 1
 df = pd.DataFrame({"user": u, "item": i, "tstamp": ts, "rating": r})

@@ -37,7 +37,7 @@ def main():
     ap.add_argument("--workload", default="ml20m")
     ap.add_argument("--what", default="gram,score")
     args = ap.parse_args()
-    shape, kwargs, desc = WORKLOADS[args.workload]
+    shape, kwargs, desc = (WORKLOADS[args.workload][k] for k in ("shape", "kwargs", "desc"))
     u, i, ts, r = load_events(shape)
     decay = kwargs.get("decay_in_days")
     rate = None if decay is None else 1.0 - (np.log(2) / decay)
@@ -70,12 +70,12 @@ def main():
             res[f"gram_v3_lower_slice{sl}_r{rg}"] = {"ms": msv, "equal": bool(torch.equal(G1, G))}
         D.set_option("gram_slice", 0); D.set_option("gram_ranges", 0)
         # experimental: segment-length guards in gram_lower_kernel
-        for mode in (1, 2):
+        for mode in (0, 1, 2):
             D.set_option("gram_adapt", mode)
             msa, _ = timeit(g3a)
             D.gram_finish(box["L"], out=G)
             res[f"gram_v3_lower_adapt{mode}"] = {"ms": msa, "equal": bool(torch.equal(G1, G))}
-        D.set_option("gram_adapt", 0)
+        D.set_option("gram_adapt", 2)
         D.gram_finish(D.gram_lower(X), out=G)
         res["gram_v3_equal"] = bool(torch.equal(G1, G))
         res["gram_v3_maxdiff"] = float((G1 - G).abs().max())

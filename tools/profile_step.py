@@ -11,7 +11,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "ml20m"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 if len(sys.argv) > 3:
     D.set_option("score_impl", int(sys.argv[3]))
-shape, kwargs, desc = bench.WORKLOADS[wl]
+shape, kwargs, desc = (bench.WORKLOADS[wl][k] for k in ("shape", "kwargs", "desc"))
 u, i, ts, r = bench.load_events(shape)
 U = int(u.max()) + 1
 op = SLIMElastic(kwargs)
