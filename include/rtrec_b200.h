@@ -257,6 +257,13 @@ typedef struct {
     int32_t nn;          /* nn_feature_selection (:190), 0 = all items are features */
     int32_t n_samples;   /* rows of X = max_user_id+1; scales the penalties (_coordinate_descent.py:781) */
     int32_t nonneg;      /* 1 iff every stored value of X is >= 0 (enables live-set pruning) */
+    int32_t skip_trivial; /* 1: with feature selection (nn > 0), a target whose Gram row holds no entry above
+                            alpha*l1_ratio*n_samples -- all nn coefficients are 0 before the first sweep -- may be returned
+                            with NO pairs (d_out_cnt = 0) instead of nn zeros, and its candidates are not selected.  Valid
+                            when the result is assembled into an empty W (a bulk fit: zeros are never stored,
+                            slim_elastic.py:273-274) and d_sel_out is not requested; a partial fit must pass 0, because a
+                            returned zero deletes a stale entry of the old matrix (:533-538).  Ignored unless positive and
+                            nonneg are set.  (All-features mode, nn == 0, returns only non-zero coefficients anyway.) */
 } rt_fit_config;
 
 /* xorshift32 draw table: out[t] = value of the (t+1)-th our_rand_r call from `seed`

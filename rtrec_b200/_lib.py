@@ -37,6 +37,7 @@ class FitConfig(C.Structure):
         ("nn", C.c_int32),
         ("n_samples", C.c_int32),
         ("nonneg", C.c_int32),
+        ("skip_trivial", C.c_int32),
     ]
 
 

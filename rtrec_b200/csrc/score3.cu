@@ -159,7 +159,7 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // sparse mode: queries without a single W entry behind their items were answered by query_work_kernel and sit at the
     // end of order[]; only the first *n_active_queries are scored here
-    if (n_active_queries) n_query = min(n_query, *n_active_queries);
+    if (n_active_queries) n_query = min(n_query, *n_active_queries);   // (the launcher passes the count of dense-tile queries)
     for (;;) {
         __syncthreads();
         if (tid == 0) sh.q = atomicAdd(next_query, 1);
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256) query_work_kernel(const int *__restrict__
                                                          const int *__restrict__ wrptr, int j_begin, int j_end, int n_items,
                                                          const int *__restrict__ wridx, int k, int sparse,
                                                          unsigned *__restrict__ keys, int *__restrict__ idx,
-                                                         int *__restrict__ n_active, int *__restrict__ out_ids,
+                                                         int *__restrict__ n_active, int sparse_cap, int *__restrict__ out_ids,
                                                          float *__restrict__ out_scores, int *__restrict__ out_cnt) {
     const int lane = threadIdx.x & 31;
     const int q = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -369,7 +369,134 @@ __global__ void __launch_bounds__(256) query_work_kernel(const int *__restrict__
         // key: work, +1 for every scored query so that only answered ones carry key 0 (they sort to the end)
         keys[q] = skip ? 0u : (unsigned)min(work + 1ull, 0xffffffffull);
         idx[q] = q;
-        if (skip) out_cnt[q] = 0; else atomicAdd(n_active, 1);
+        // n_active[0] = queries with work, n_active[1] = those among them that go to the dense-tile kernel (the rest, with
+        // at most sparse_cap entries behind their items, are scored by recommend_sparse_kernel)
+        if (skip) out_cnt[q] = 0;
+        else {
+            atomicAdd(n_active, 1);
+            if (sparse_cap < 0 || work > (unsigned long long)sparse_cap) atomicAdd(n_active + 1, 1);   // < 0: no sparse kernel
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Queries with little work (sparse top-k semantics only): the scores of a user whose items have at most SP_CAP stored W
+// entries behind them touch at most SP_CAP items, so a dense score tile (zeroing and scanning tens of thousands of floats
+// per user and item range) is the wrong structure.  One warp per query accumulates into a small open-addressing table
+// in shared memory.  Rows of W are applied one after the other in ascending item order with separate fp32 multiply and
+// add -- the first touch of an item stores x*w (= 0 + x*w) -- so every score is bit-identical to the dense-tile kernels'
+// and to scipy's csr_matmat sum.  Selection: k rounds of a warp arg-max with the usual order (score desc, item id desc).
+// Serves W matrices with few columns (all-features fits at the H&M shape end with a handful of entries) and the long
+// tail of users with a few ratings.
+constexpr int SP_SLOTS = 2048;
+constexpr int SP_CAP = 1024;
+constexpr int SP_WARPS = 4;
+constexpr int SP_KMAX = 32;
+
+__device__ __forceinline__ int sp_hash(int j) { return (int)(((unsigned)j * 2654435761u) >> 21) & (SP_SLOTS - 1); }
+
+__global__ void __launch_bounds__(SP_WARPS * 32)
+recommend_sparse_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, const float *__restrict__ rval,
+                        const int *__restrict__ users, const int *__restrict__ order, const int *__restrict__ n_active,
+                        const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
+                        int n_items, int j_begin, int j_end, int k, int filter, int *__restrict__ out_ids,
+                        float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ next_query) {
+    extern __shared__ __align__(16) int sp_smem[];   // per warp: SP_SLOTS keys, then SP_SLOTS values
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *key = sp_smem + (size_t)warp * 2 * SP_SLOTS;
+    float *val = reinterpret_cast<float *>(key + SP_SLOTS);
+    const int q_end = n_active[0], q_begin = n_active[1];   // order[q_begin .. q_end): the queries of this kernel
+    const bool whole = j_begin == 0 && j_end == n_items;
+    for (;;) {
+        int qi = 0;
+        if (lane == 0) qi = q_begin + atomicAdd(next_query, 1);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= q_end) break;
+        const int q = order[qi];
+        const int u = users[q];
+        const int r0 = rptr[u], r1 = rptr[u + 1];
+        for (int s = lane; s < SP_SLOTS; s += 32) key[s] = -1;
+        __syncwarp();
+        // ---- accumulate, row by row in ascending item order
+        for (int c0 = r0; c0 < r1; c0 += 32) {
+            const int p = c0 + lane;
+            int a = 0, b = 0;
+            float x = 0.f;
+            if (p < r1) {
+                const int i = ridx[p];
+                x = rval[p];
+                a = wrptr[i]; b = wrptr[i + 1];
+                if (!whole && b > a) { a = lower_bound3(wridx, a, b, j_begin); b = lower_bound3(wridx, a, b, j_end); }
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, b > a);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int al = __shfl_sync(0xffffffffu, a, l), bl = __shfl_sync(0xffffffffu, b, l);
+                const float xl = __shfl_sync(0xffffffffu, x, l);
+                for (int e = al + lane; e < bl; e += 32) {
+                    const int j = wridx[e];
+                    const float add = __fmul_rn(xl, wrval[e]);
+                    int slot = sp_hash(j);
+                    int prev;
+                    for (;;) {
+                        prev = atomicCAS(&key[slot], -1, j);
+                        if (prev == -1 || prev == j) break;
+                        slot = (slot + 1) & (SP_SLOTS - 1);
+                    }
+                    // items of one W row are distinct, so no two lanes update the same slot between two __syncwarp()s
+                    val[slot] = prev == -1 ? __fadd_rn(0.0f, add) : __fadd_rn(val[slot], add);
+                }
+                __syncwarp();
+            }
+        }
+        // ---- interacted items leave the table
+        if (filter) {
+            for (int p = r0 + lane; p < r1; p += 32) {
+                const int i = ridx[p];
+                if (i < j_begin || i >= j_end) continue;
+                int slot = sp_hash(i);
+                for (;;) {
+                    const int kk = key[slot];
+                    if (kk == -1) break;
+                    if (kk == i) { val[slot] = 0.0f; break; }   // a zero score is not eligible in sparse mode
+                    slot = (slot + 1) & (SP_SLOTS - 1);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- top-k: k rounds of arg-max over the table, order (score desc, item id desc); taken entries are cleared
+        int cnt = 0;
+        for (int round = 0; round < k; ++round) {
+            uint32_t bk = 0u;
+            int bi = -1, bs = -1;
+            for (int s = lane; s < SP_SLOTS; s += 32) {
+                const int kk = key[s];
+                if (kk < 0) continue;
+                const float v = val[s];
+                if (v == 0.0f) continue;
+                const uint32_t fk = float_key(v);
+                if (fk > bk || (fk == bk && kk > bi)) { bk = fk; bi = kk; bs = s; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint32_t ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (ok > bk || (ok == bk && oi > bi)) { bk = ok; bi = oi; bs = os; }
+            }
+            if (bi < 0) break;
+            if (lane == 0) {
+                out_ids[(size_t)q * k + round] = bi;
+                out_scores[(size_t)q * k + round] = key_to_float3(bk);
+                val[bs] = 0.0f;
+            }
+            ++cnt;
+            __syncwarp();
+        }
+        for (int e = cnt + lane; e < k; e += 32) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+        if (lane == 0) out_cnt[q] = cnt;
+        __syncwarp();
     }
 }
 
@@ -501,6 +628,7 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
     int grid = rt::sm_count() * per_sm;
     if (grid > n_query) grid = n_query;
     const int *d_order = nullptr, *d_n_active = nullptr;
+    bool use_sparse = false;
     if (n_query > 4 * grid) {
         // heaviest-query-first processing order; in sparse mode queries without work are answered on the spot
         const size_t nq = (size_t)n_query;
@@ -508,15 +636,26 @@ extern "C" int rt_slim_recommend_packed(const int32_t *d_rptr, const int32_t *d_
         if (!keys) return RT_ERR_CUDA;
         unsigned *keys2 = keys + nq + 32;
         int *idx = (int *)(keys2 + nq + 32), *idx2 = idx + nq + 32;
-        int *d_cnt_active = d_next + 8;
-        RT_CUDA(cudaMemsetAsync(d_cnt_active, 0, sizeof(int), st));
+        int *d_cnt_active = d_next + 8;            // [0] queries with work, [1] dense-tile queries among them
+        RT_CUDA(cudaMemsetAsync(d_next, 0, 64, st));
+        // the sparse-table kernel takes queries with little work when the semantics allow it (sparse top-k, k <= 32)
+        use_sparse = mode == RT_TOPK_SPARSE && k <= SP_KMAX && rt::option(rt::OPT_SCORE_IMPL) != 1;
         query_work_kernel<<<(unsigned)(((int64_t)n_query * 32 + 255) / 256), 256, 0, st>>>(
             d_rptr, d_ridx, d_users, n_query, d_wrptr, j_begin, j_end, n_items, d_wridx, k, mode == RT_TOPK_SPARSE ? 1 : 0, keys, idx,
-            d_cnt_active, d_out_ids, d_out_scores, d_out_cnt);
+            d_cnt_active, use_sparse ? SP_CAP : -1, d_out_ids, d_out_scores, d_out_cnt);
         RT_CHECK_LAUNCH();
         S3_CUB(cub::DeviceRadixSort::SortPairsDescending(d_tmp__, tmp_bytes__, keys, keys2, idx, idx2, n_query, 0, 32, st));
         d_order = idx2;
-        d_n_active = d_cnt_active;
+        d_n_active = d_cnt_active + 1;
+        if (use_sparse) {
+            const int sgrid = rt::sm_count() * 3;
+            const size_t ssmem = (size_t)SP_WARPS * 2 * SP_SLOTS * sizeof(int);
+            RT_CUDA(cudaFuncSetAttribute(recommend_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            recommend_sparse_kernel<<<sgrid, SP_WARPS * 32, ssmem, st>>>(d_rptr, d_ridx, d_rval, d_users, d_order, d_cnt_active, d_wrptr,
+                                                                   d_wridx, d_wrval, n_items, j_begin, j_end, k, filter_interacted,
+                                                                   d_out_ids, d_out_scores, d_out_cnt, d_next + 4);
+            RT_CHECK_LAUNCH();
+        }
     }
     recommend3_kernel<<<grid, S3_NT, smem, st>>>(
         d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of, d_ell_off, (const int2 *)d_ell, n_tiles,

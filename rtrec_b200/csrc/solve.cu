@@ -50,6 +50,7 @@ struct SolveArgs {
     size_t scratch_per_cta;
     const int *only_flagged;  // when set, the block kernel solves only targets t with only_flagged[t] != 0
     int flag_mod;             // test hook (solve_impl = 3): the warp kernel hands every flag_mod-th target to the block kernel
+    int skip_trivial;  // nn mode: targets without a live coordinate return no pairs (rt_fit_config.skip_trivial)
     int hot_in_smem;  // per-visit arrays live in dynamic shared memory
     int use_gs;       // dense live x live Gram block cached in shared memory (nn mode)
 };
@@ -536,6 +537,20 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
                     const int c = i & 3;
                     bm[0] = c == 0 ? fmaxf(bm[0], v) : bm[0]; bm[1] = c == 1 ? fmaxf(bm[1], v) : bm[1];
                     bm[2] = c == 2 ? fmaxf(bm[2], v) : bm[2]; bm[3] = c == 3 ? fmaxf(bm[3], v) : bm[3];
+                }
+            }
+            if (A.skip_trivial) {
+                // largest feature score of the row = largest bucket maximum: nothing above the L1 threshold -> w = 0 with a
+                // duality gap of exactly 0 before the first sweep; the column is finished here (no candidate pass)
+                float rm = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rm = fmaxf(rm, __shfl_xor_sync(0xffffffffu, rm, o));
+                if (!((double)rm > a)) {
+                    if (lane == 0) {
+                        A.out_off[t] = (int64_t)t * NU; A.out_cnt[t] = 0;
+                        if (A.stats) { A.stats[(size_t)t * 4 + 0] = 0; A.stats[(size_t)t * 4 + 1] = 0; A.stats[(size_t)t * 4 + 2] = 1; A.stats[(size_t)t * 4 + 3] = 0; }
+                    }
+                    continue;
                 }
             }
             const int kk = min(NU, N);
@@ -1046,6 +1061,7 @@ static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t
     A.scratch_per_cta = p.scratch_per_cta;
     A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
     A.only_flagged = nullptr;
+    A.skip_trivial = (cfg->nn > 0 && cfg->skip_trivial && cfg->positive && cfg->nonneg && !d_sel_out && !d_sel_in) ? 1 : 0;
     A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;
     RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
     A.diag = nullptr;

@@ -83,19 +83,16 @@ class BaseModel(ABC):
         try:
             user_ids = self.user_ids.identify_many(users)
             item_ids = self.item_ids.identify_many(items)
-            ts = np.asarray(tstamps, dtype=np.float64)
-            rt = np.asarray(ratings, dtype=np.float64)
-            if len(user_ids) and (min(int(user_ids.min()), int(item_ids.min())) < 0
-                                  or max(int(user_ids.max()), int(item_ids.max())) > _INT32_MAX):
-                raise ValueError("ids outside [0, 2^31)")
-        except Exception as e:  # noqa: BLE001
-            # something in the columns is malformed: replay them event by event, so that only the offending events are
-            # skipped with a warning (base.py:85-94) instead of the whole batch raising
+            # (the store validates the id ranges itself -- on the device for large batches -- before it changes state)
+            self.interactions.add_interactions_batch(user_ids, item_ids, np.asarray(tstamps, dtype=np.float64),
+                                                     np.asarray(ratings, dtype=np.float64), upsert=update_interaction)
+        except (ValueError, TypeError) as e:
+            # something in the columns is malformed (mixed id kinds, an id outside [0, 2^31), a non-numeric rating):
+            # replay them event by event, so that only the offending events are skipped with a warning (base.py:85-94)
             logging.warning(f"Column ingest fell back to the per-event path: {e}")
             self.add_interactions(zip(list(users), list(items), list(tstamps), list(ratings)),
                                   update_interaction=update_interaction, record_interactions=record_interactions)
             return
-        self.interactions.add_interactions_batch(user_ids, item_ids, ts, rt, upsert=update_interaction)
         if record_interactions:
             self._record_interaction_arrays(user_ids, item_ids)
 

@@ -103,12 +103,15 @@ class SLIMElastic:
             raise NotImplementedError("optim='sgd' (SGDRegressor, slim_elastic.py:209-222) is not on the accelerated path")
         raise ValueError(f"Invalid Optimizer name: {self.optim_name}")
 
-    def _config(self, X: D.DeviceMatrix) -> FitConfig:
+    def _config(self, X: D.DeviceMatrix, into_empty_w: bool = True) -> FitConfig:
+        """``into_empty_w``: the result will be assembled into an empty W (bulk fit) -- columns that are zero before the first
+        sweep may then come back without their nn zero coefficients (rt_fit_config.skip_trivial); a merge into an existing
+        W needs them (a returned zero deletes a stale entry, slim_elastic.py:533-538)."""
         nn = int(self.nn_feature_selection) if self.nn_feature_selection is not None else 0
         return FitConfig(alpha=float(self.alpha), l1_ratio=float(self.l1_ratio), tol=float(self.tol),
                          max_iter=int(self.max_iter), positive=1 if self.positive_only else 0,
                          seed=sklearn_seed(self.random_state), nn=nn, n_samples=int(X.n_users),
-                         nonneg=1 if X.nonneg else 0)
+                         nonneg=1 if X.nonneg else 0, skip_trivial=1 if into_empty_w else 0)
 
     @staticmethod
     def _as_device(interaction_matrix, allow=("csc", "csr"), err="Interaction matrix must be a scipy.sparse.csr_matrix or scipy.sparse.csc_matrix.") -> D.DeviceMatrix:
@@ -131,7 +134,8 @@ class SLIMElastic:
     def _fit_device(self, X: D.DeviceMatrix, targets: np.ndarray, keep_old: bool, sel_in: Optional[np.ndarray] = None):
         """gram -> solve -> merge.  ``targets``: item ids (host int array)."""
         t = D.require_cuda()
-        cfg = self._config(X)
+        old = self._device_W() if keep_old else None
+        cfg = self._config(X, into_empty_w=(old is None or old.nnz == 0))
         n_items = X.n_items
         tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
         res = None
@@ -151,7 +155,6 @@ class SLIMElastic:
                 sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))
             res = D.solve(G, n_items, tg, cfg, sel_in=sel_dev, want_sel=self.keep_fit_details)
             del G
-        old = self._device_W() if keep_old else None
         self._W = D.w_merge(old, n_items, res)
         self._W_host = None
         if self.keep_fit_details:

@@ -40,19 +40,21 @@ def oracle_columns(Xc, cols, nn, sel=None):
     return so.SlimOracle._to_csc(colsd, Xc.shape[1])
 
 
-def stratified_columns(W, Xc, rng, per_decile_nontrivial=16, per_decile_any=10, among=None):
-    """columns by popularity decile (stored entries of the column): some whose device solution is not all zero, some at random"""
+def stratified_columns(W, Xc, rng, n_nontrivial=160, per_decile_any=12, among=None):
+    """columns by popularity (stored entries of the column): ``n_nontrivial`` whose device solution is not all zero, spread
+    over the popularity deciles of those columns, plus ``per_decile_any`` random columns of every popularity decile"""
     I = Xc.shape[1]
     pool = np.arange(I) if among is None else np.asarray(among)
     cl = np.diff(Xc.indptr)[pool]
     order = pool[np.argsort(-cl, kind="stable")]
     nz = np.diff(W.indptr) > 0
+    nt = order[nz[order]]
     picks = []
     for d in range(10):
+        a, b = len(nt) * d // 10, len(nt) * (d + 1) // 10
+        if b > a:
+            picks.append(rng.choice(nt[a:b], min(n_nontrivial // 10, b - a), replace=False))
         dec = order[len(order) * d // 10: len(order) * (d + 1) // 10]
-        nt = dec[nz[dec]]
-        if len(nt):
-            picks.append(rng.choice(nt, min(per_decile_nontrivial, len(nt)), replace=False))
         picks.append(rng.choice(dec, min(per_decile_any, len(dec)), replace=False))
     return np.unique(np.concatenate(picks)).astype(np.int32)
 
@@ -196,7 +198,7 @@ def test_c4_streaming_partial_fit_full_size(c2):
         # ---- re-solved columns against the oracle on the matrix that holds only the touched columns (slim.py:48-53)
         Xm = so.state_to_matrix(state, fmt="csc", select_items=touched.tolist())
         assert sorted(int(t) for t in m.model.last_fit_targets) == touched.tolist()
-        cols = stratified_columns(W, Xm, rng, per_decile_nontrivial=8, per_decile_any=4, among=touched)
+        cols = stratified_columns(W, Xm, rng, n_nontrivial=80, per_decile_any=4, among=touched)
         Wo = oracle_columns(Xm, cols, 50, sel=device_sel(m, cols))
         # the reference's merge keeps old entries of a re-solved column that the new solve does not return (slim_elastic.py
         # :533-538 assigns only the returned candidates): compare on the candidates of the new solve
@@ -281,7 +283,7 @@ def test_c3_hm_nn50_full_size(hm_events, hm_oracle_matrix):
     W = m.model.item_similarity.tocsc()
     assert (W.data > 0).all() and (W.diagonal() == 0).all() and np.diff(W.indptr).max() <= 50
     rng = np.random.default_rng(4)
-    cols = stratified_columns(W, Xo, rng, per_decile_nontrivial=12, per_decile_any=4)
+    cols = stratified_columns(W, Xo, rng, n_nontrivial=120, per_decile_any=4)
     Wo = oracle_columns(Xo, cols, 50, sel=device_sel(m, cols))
     rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, nn=50")
     print(f"\n[c3 nn50] nnz(W) = {W.nnz}, {len(cols)} columns compared ({int((np.diff(W.indptr)[cols] > 0).sum())} non-trivial), worst {rel[cols].max():.3e}")

@@ -285,6 +285,95 @@ def test_predict_family_matches_scipy(golden):
         m.predict(X.shape[0], X)
 
 
+@pytest.mark.parametrize("nn", [20, None])
+def test_trivial_columns_shortcut_gives_the_same_w(nn):
+    """Targets whose Gram row has no entry above the L1 threshold are zero before the first sweep.  Bulk fits return them
+    without pairs (nn mode: rt_fit_config.skip_trivial, decided after the first pass over the row; all features: the
+    prefilter kernel); W, and the stats of every column, equal the full path's."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    U, I, N = 30000, 1200, 150000
+    u, i, ts, r = synth_events(U, I, N, seed=8, rating="half")          # a = 0.01 * 30000 = 300: most columns are trivial
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    dX = D.DeviceMatrix.from_scipy(X)
+    G = D.gram_full(dX)
+    tg = torch.arange(I, dtype=torch.int32, device="cuda")
+    op = SLIMElastic({"nn_feature_selection": nn} if nn else {})
+    outs = []
+    try:
+        for fast in (True, False):
+            D.set_option("solve_impl", 2 if fast else 1)               # 1 = CTA kernel for everything, no shortcut
+            res = D.solve(G, I, tg, op._config(dX, into_empty_w=fast))
+            W = D.w_merge(None, I, res)
+            outs.append((W.to_scipy_csc(), res.stats.cpu().numpy(), res.cnt.cpu().numpy()))
+    finally:
+        D.set_option("solve_impl", 2)
+    (Wa, sa, ca), (Wb, sb, cb) = outs
+    assert 0 < Wb.nnz and (np.diff(Wb.indptr) == 0).mean() > 0.3, "the case must mix trivial and non-trivial columns"
+    assert np.array_equal(Wa.indptr, Wb.indptr) and np.array_equal(Wa.indices, Wb.indices)
+    triv = sb[:, 3] == 0
+    assert np.array_equal(sa[triv], sb[triv]) and (sb[triv] == np.array([0, 0, 1, 0])).all()
+    if nn:
+        assert (ca[triv] == 0).all() and (cb == nn).all()
+        # warp kernel vs CTA kernel on the non-trivial columns: the same bar as test_warp_solver_equals_block_solver
+        assert np.abs(Wa.data - Wb.data).max() <= 1e-3 * np.abs(Wb.data).max()
+    else:
+        assert np.array_equal(Wa.data, Wb.data)
+
+
+@pytest.mark.parametrize("j_range", [None, (400, 2300)])
+def test_sparse_table_and_zero_work_queries_equal_dense_tile(j_range):
+    """Large batches are split by work (score3.cu): queries with no W entry behind their items are answered without a
+    launch of their own, queries with <= 1,024 entries go to the sparse-table kernel (one warp per query), the rest to the
+    dense-tile kernel.  Sparse top-k semantics, ids / scores / counts bit-identical to the v2 kernel, which knows none of
+    this; dense semantics (zeros eligible) must not take the shortcut."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200._lib import RT_TOPK_DENSE, RT_TOPK_SPARSE
+    rng = np.random.default_rng(17)
+    n_items, n_users = 3000, 6000
+    # W: rows of items < 1000 are empty, 1000..2499 hold a few entries, 2500.. are long
+    rows, cols, vals = [], [], []
+    for i in range(1000, 2500):
+        c = rng.choice(n_items, int(rng.integers(1, 9)), replace=False)
+        rows.append(np.full(len(c), i)); cols.append(c); vals.append(rng.random(len(c)).astype(np.float32))
+    for i in range(2500, n_items):
+        c = rng.choice(n_items, int(rng.integers(200, 900)), replace=False)
+        rows.append(np.full(len(c), i)); cols.append(c); vals.append(rng.random(len(c)).astype(np.float32))
+    W = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_items, n_items))
+    # users: a third only rate items with empty rows (no work), a third a few light items, a third also heavy items
+    xr, xc = [], []
+    for u in range(n_users):
+        kind = u % 3
+        its = rng.choice(1000, int(rng.integers(1, 30)), replace=False)
+        if kind >= 1:
+            its = np.concatenate([its, 1000 + rng.choice(1500, int(rng.integers(1, 60)), replace=False)])
+        if kind == 2:
+            its = np.concatenate([its, 2500 + rng.choice(500, int(rng.integers(2, 40)), replace=False)])
+        xr.append(np.full(len(its), u)); xc.append(its)
+    xr, xc = np.concatenate(xr), np.concatenate(xc)
+    X = sp.csr_matrix((rng.integers(1, 11, len(xr)).astype(np.float32) * 0.5, (xr, xc)), shape=(n_users, n_items))
+    dX, dW = D.DeviceMatrix.from_scipy(X), D.DeviceW.from_scipy(W)
+    users = torch.from_numpy(rng.permutation(n_users).astype(np.int32)).cuda()
+    j0, j1 = (0, n_items) if j_range is None else j_range
+    try:
+        for mode in (RT_TOPK_SPARSE, RT_TOPK_DENSE):
+            for filt in (True, False):
+                for k in (10, 40):      # k = 40 > 32: the sparse-table kernel is not used
+                    D.set_option("score_impl", 2)
+                    a = [x.cpu().numpy() for x in D.recommend(dX, users, dW, k, filt, mode, j0, j1)]
+                    D.set_option("score_impl", 3)
+                    b = [x.cpu().numpy() for x in D.recommend(dX, users, dW, k, filt, mode, j0, j1)]
+                    for x, y in zip(a, b):
+                        assert np.array_equal(x, y), (mode, filt, k)
+                    if mode == RT_TOPK_SPARSE:
+                        cnt = b[2][np.argsort(users.cpu().numpy())]
+                        assert (cnt[0::3] == 0).all() and (cnt[2::3] > 0).all()
+    finally:
+        D.set_option("score_impl", 3)
+
+
 # ------------------------------------------------------------------------------------------ fit
 @pytest.mark.parametrize("name,cfg", FIT_CASES)
 def test_fit_matches_reference_golden(golden, name, cfg):
