@@ -400,6 +400,34 @@ int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d
                     float *d_out_scores, int32_t *d_out_cnt, void *stream);
 
 /*
+ * Scoring with the heavy rows of W on the tensor cores (score_tc.cu; same contract as rt_slim_recommend_packed --
+ * slim_elastic.py:674-818 -- over the WHOLE item range, for k <= 16, but scores agree with the fp32 reference sums only to
+ * ~1e-6 relative: top-k lists match up to ties within tolerance).  Preconditions, checked by the caller: every stored value
+ * of W and of X is >= 0 (a light contribution can then only raise a score), at most 64 heavy rows.
+ *   rt_tc_pack_size / rt_tc_pack_build: per W, the heavy rows (d_heavy_list[n_heavy], ascending item id = heavy slot, as
+ *     rt_w_pack_plan numbers them) as three K-major bf16 planes d_bt[3][i_pad][64] (w = w0 + w1 + w2; TMA source, 128-byte
+ *     aligned) and as dense fp32 rows d_wd[n_heavy][n_items]; *h_w_nonneg = 1 iff no stored value of W is negative.
+ *     Synchronises.
+ *   rt_values_bf16_exact: are all n values >= 0 / exactly representable in bf16 (integer and half-integer ratings are:
+ *     one operand plane instead of three).  Synchronises.
+ *   rt_slim_recommend_tc: x_planes = 1 or 3 (see above); d_tc_* [n_query, 16] / [n_query] receive the heavy-only candidate
+ *     lists of the tensor-core kernel, d_out_* the final lists (as rt_slim_recommend_packed), d_fallback[n_query] != 0
+ *     marks queries the fast path could not finish (the caller re-scores them with rt_slim_recommend_packed);
+ *     d_dbg_scores (optional, [n_query, i_pad]) receives every heavy-only score (tests).  Needs an sm_100 device.
+ */
+int rt_tc_pack_size(int32_t n_items, int32_t n_heavy, int32_t *h_i_pad, int64_t *h_bt_bytes, int64_t *h_wd_bytes);
+int rt_tc_pack_build(const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval, int64_t w_nnz,
+                     int32_t n_items, const int32_t *d_heavy_list, int32_t n_heavy, void *d_bt, float *d_wd,
+                     int32_t *h_w_nonneg, void *stream);
+int rt_values_bf16_exact(const float *d_vals, int64_t n, int32_t *h_nonneg, int32_t *h_bf16_exact, void *stream);
+int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval, const int32_t *d_users,
+                         int32_t n_query, const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval,
+                         const int32_t *d_heavy_of, const void *d_bt, const float *d_wd, int32_t n_items, int32_t k,
+                         int32_t filter_interacted, int32_t mode, int32_t x_planes, int32_t *d_tc_ids,
+                         float *d_tc_scores, int32_t *d_tc_cnt, int32_t *d_out_ids, float *d_out_scores,
+                         int32_t *d_out_cnt, int32_t *d_fallback, float *d_dbg_scores, void *stream);
+
+/*
  * Host-side replay of LRUFreqSet.add (lru.py:33-47; one call per event with delta > 0, interactions.py:115-116) for a
  * batch in which evictions can occur: h_values[n] non-negative integer keys < key_bound in arrival order, the current set
  * as h_in_keys / h_in_counts[n_in] in least- to most-recently-used order; the new set comes back the same way

@@ -1,0 +1,705 @@
+// score_tc.cu -- K6 (v4): scoring with the heavy rows of W on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces /root/reference/rtrec/models/internal/slim_elastic.py:674-741 (recommend_batch: safe_sparse_dot + per-user
+// top-k), :743-779 and :781-818 for large batches, like score3.cu, but NOT bit for bit: scores agree with the fp32
+// reference sums to ~1e-6 relative, so top-k lists agree up to ties within tolerance (north_star section 6; the exact
+// kernels of score3.cu remain the default for small batches, for item-sharded scoring and whenever a precondition fails).
+//
+// Why (profiles/r2c_ml20m_recommend3.md): at the ML-20M shape 99 % of the multiply-adds of X.W come from ~50
+// source items whose W rows hold thousands of entries.  That part of the product is a dense contraction
+//     S_h[U x I] = X_h[U x 64] . W_h[64 x I]
+// which the exact kernels execute as 1.2e10 shared-memory read-modify-writes (L1/TEX bound, 14.3 ms).  Here:
+//   * W_h is stored once per W as three bf16 planes (w = w0 + w1 + w2, 24 mantissa bits), K-major, and streamed by TMA
+//     (cp.async.bulk.tensor, 128-byte swizzle) through a 3-stage mbarrier ring;
+//   * X_h of 128 users is gathered from the CSR rows into a swizzled shared-memory operand (values that are exact in
+//     bf16 -- integer and half-integer ratings -- need one plane, decayed values three);
+//   * tcgen05.mma (M=128, N=128, K=16, fp32 accumulate) forms the split products x0w0 + x0w1 + x0w2 (+ x1w0 + x1w1 +
+//     x2w0) into one of four TMEM accumulators;
+//   * the epilogue warps read the accumulators with tcgen05.ld, drop the user's interacted items (a bit mask built from
+//     the row cursor) and keep a threshold top-k per TMEM lane -- the score matrix never exists anywhere.
+// The light rows of W (1 % of the multiply-adds, but they touch arbitrary cells) are added by recommend_tcfix_kernel on
+// the CUDA cores: with W >= 0 and X >= 0 a light contribution can only raise a score, so the final top-k is contained in
+// (heavy-only top-k) U (cells touched by light rows); those cells are accumulated in a shared-memory hash table (64-bit
+// fixed point: deterministic whatever the order), completed with their heavy part from a dense fp32 copy of W_h, and
+// merged with the tensor-core list.  Users whose table would overflow, or who end with fewer than k positive scores in
+// dense mode, are flagged and re-scored by the exact kernel.
+//
+// Algorithmic bytes per user: e*nnz(row u) + e*sum_{i in row u} nnz(W[i,:]) + 8k.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace rt {
+
+constexpr int TC_M = 128;        // users per CTA tile (= TMEM lanes)
+constexpr int TC_N = 128;        // items per accumulator tile (= TMEM columns per buffer)
+constexpr int TC_KH = 64;        // heavy rows (K of one operand tile: 64 bf16 = one 128-byte swizzle row)
+constexpr int TC_STAGES = 3;     // W_h ring
+constexpr int TC_ACC = 4;        // TMEM accumulator buffers (4 x 128 = 512 columns)
+constexpr int TC_KLIST = 16;     // longest list kept per user
+constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: operand gather + epilogue
+constexpr int TC_TILE_BYTES = TC_N * TC_KH * 2;   // one [128 rows x 64 bf16] operand tile
+
+struct TcParams {
+    const int *rptr, *ridx;
+    const float *rval;
+    const int *users;
+    int n_query;
+    const int *heavy_of;     // item -> heavy slot (< TC_KH) or -1
+    int n_tiles, i_pad;      // item tiles of TC_N, padded item count
+    int k, filter;
+    int *out_ids;            // [n_query, TC_KLIST] heavy-only candidates (unsorted)
+    float *out_scores;
+    int *out_cnt;
+    float *dbg;              // optional [n_query, i_pad]: every heavy-only score (tests)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// parity wait; a barrier that never completes (a protocol bug) traps after ~2 s instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned spins = 0;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++spins & 0x3ff) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// shared-memory matrix descriptor of a K-major operand tile in the 128-byte swizzle layout (rows of 64 bf16 = 128 B, groups of
+// 8 rows 1024 B apart): start address, LBO (unused with swizzle) = 1, SBO = 1024 B, descriptor version 1, layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t addr) {
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of element (row, k) inside a swizzled operand tile (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8)
+__device__ __forceinline__ int tc_sw_off(int row, int k) {
+    const int chunk = (k >> 3) ^ (row & 7);
+    return row * 128 + chunk * 16 + (k & 7) * 2;
+}
+
+// threshold list of one user: unsorted, smallest member = thr once the list holds k entries.  Returns the new (n, thr)
+// by value so that both stay in registers at the call sites.
+struct TcListState { int n; float thr; };
+__device__ __noinline__ TcListState tc_insert(float v, int j, float *ls, int *li, int n, float thr, int k) {
+    if (n < k) {
+        ls[n * TC_M] = v; li[n * TC_M] = j;
+        ++n;
+        if (n < k) return {n, thr};
+    } else {
+        int s = 0;
+        while (s < k - 1 && ls[s * TC_M] != thr) ++s;
+        ls[s * TC_M] = v; li[s * TC_M] = j;
+    }
+    float m = ls[0];
+    for (int s = 1; s < k; ++s) m = fminf(m, ls[s * TC_M]);
+    return {n, m};
+}
+
+template <int SX>
+__global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    // operand tiles need 1024-byte alignment (swizzle atom); everything else lives behind them
+    unsigned char *smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+    unsigned char *sA = smem;                                         // SX tiles
+    unsigned char *sB = sA + SX * TC_TILE_BYTES;                      // TC_STAGES x 3 tiles
+    float *list_s = reinterpret_cast<float *>(sB + TC_STAGES * 3 * TC_TILE_BYTES);
+    int *list_i = reinterpret_cast<int *>(list_s + TC_KLIST * TC_M);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(list_i + TC_KLIST * TC_M);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const uint32_t bar0 = smem_u32(bars);
+    auto b_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto b_empty = [&](int s) { return bar0 + 8u * (uint32_t)(TC_STAGES + s); };
+    auto acc_full = [&](int b) { return bar0 + 8u * (uint32_t)(2 * TC_STAGES + b); };
+    auto acc_empty = [&](int b) { return bar0 + 8u * (uint32_t)(2 * TC_STAGES + TC_ACC + b); };
+    const uint32_t a_full = bar0 + 8u * (uint32_t)(2 * TC_STAGES + 2 * TC_ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int b = 0; b < TC_ACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+        mbar_init(a_full, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_blocks = (P.n_query + TC_M - 1) / TC_M;
+    const int NT = P.n_tiles;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        if (warp == 0) {
+            // ===== TMA producer: the three bf16 planes of one item tile per stage
+            if (lane == 0) {
+                for (int t = 0; t < NT; ++t) {
+                    const int g = it * NT + t, s = g % TC_STAGES;
+                    mbar_wait(b_empty(s), ((g / TC_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(b_full(s), 3 * TC_TILE_BYTES);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl)
+                        tma_load_2d(smem_u32(sB + (s * 3 + pl) * TC_TILE_BYTES), &tmap, b_full(s), 0, pl * P.i_pad + t * TC_N);
+                }
+            }
+        } else if (warp == 1) {
+            // ===== MMA issuer (one thread)
+            if (lane == 0) {
+                mbar_wait(a_full, it & 1);
+                tc_fence_after();
+                for (int t = 0; t < NT; ++t) {
+                    const int g = it * NT + t, s = g % TC_STAGES, b = g % TC_ACC;
+                    mbar_wait(acc_empty(b), ((g / TC_ACC) & 1) ^ 1);
+                    mbar_wait(b_full(s), (g / TC_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(b * TC_N);
+                    uint32_t acc = 0;
+                    // split products in decreasing magnitude: x0w0, x0w1, x1w0, x0w2, x1w1, x2w0 (the last three only with SX = 3)
+#pragma unroll
+                    for (int xa = 0; xa < SX; ++xa) {
+#pragma unroll
+                        for (int wb = 0; wb < 3 - xa; ++wb) {
+                            const uint32_t a_addr = smem_u32(sA + xa * TC_TILE_BYTES);
+                            const uint32_t b_addr = smem_u32(sB + (s * 3 + wb) * TC_TILE_BYTES);
+#pragma unroll
+                            for (int k4 = 0; k4 < TC_KH / 16; ++k4) {
+                                umma_bf16(d, umma_desc_k128(a_addr + k4 * 32), umma_desc_k128(b_addr + k4 * 32), acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    umma_commit(b_empty(s));     // the stage may be refilled once these MMAs have read it
+                    umma_commit(acc_full(b));    // ... and the accumulator is complete
+                }
+            }
+        } else {
+            // ===== operand gather + epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = users of those rows
+            const int quad = warp & 3;
+            const int row = quad * 32 + lane;
+            // ---- X_h of the 128 users -> swizzled A tile(s): one user at a time per warp, lanes stride over its CSR row
+            for (int uu = 0; uu < 32; ++uu) {
+                const int r = quad * 32 + uu;
+                const int q = blk * TC_M + r;
+                if (lane < 8) {
+#pragma unroll
+                    for (int xa = 0; xa < SX; ++xa)
+                        *reinterpret_cast<uint4 *>(sA + xa * TC_TILE_BYTES + r * 128 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncwarp();
+                if (q < P.n_query) {
+                    const int u = P.users[q];
+                    for (int p = P.rptr[u] + lane; p < P.rptr[u + 1]; p += 32) {
+                        const int h = P.heavy_of[P.ridx[p]];
+                        if (h >= 0) {
+                            const float x = P.rval[p];
+                            const int off = tc_sw_off(r, h);
+                            const __nv_bfloat16 x0 = __float2bfloat16_rn(x);
+                            *reinterpret_cast<__nv_bfloat16 *>(sA + off) = x0;
+                            if (SX == 3) {
+                                const float r1 = x - __bfloat162float(x0);
+                                const __nv_bfloat16 x1 = __float2bfloat16_rn(r1);
+                                const __nv_bfloat16 x2 = __float2bfloat16_rn(r1 - __bfloat162float(x1));
+                                *reinterpret_cast<__nv_bfloat16 *>(sA + TC_TILE_BYTES + off) = x1;
+                                *reinterpret_cast<__nv_bfloat16 *>(sA + 2 * TC_TILE_BYTES + off) = x2;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full);
+
+            // ---- epilogue
+            const int q = blk * TC_M + row;
+            const bool live = q < P.n_query;
+            int r_cur = 0, r_end = 0;
+            if (live && P.filter) { const int u = P.users[q]; r_cur = P.rptr[u]; r_end = P.rptr[u + 1]; }
+            float *ls = list_s + row;
+            int *li = list_i + row;
+            int n = 0;
+            float thr = 0.0f;    // scores are >= 0 (W >= 0, X >= 0): only positive ones are candidates
+            const int k = P.k;
+            for (int t = 0; t < NT; ++t) {
+                const int g = it * NT + t, b = g % TC_ACC;
+                const int t0 = t * TC_N;
+                // interacted items of this tile as a 128-bit mask (the row is ascending: a cursor walks it once per block)
+                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                while (r_cur < r_end) {
+                    const int c = P.ridx[r_cur] - t0;
+                    if (c >= TC_N) break;
+                    const uint32_t bit = 1u << (c & 31);
+                    const int w = c >> 5;
+                    m0 |= w == 0 ? bit : 0u; m1 |= w == 1 ? bit : 0u; m2 |= w == 2 ? bit : 0u; m3 |= w == 3 ? bit : 0u;
+                    ++r_cur;
+                }
+                mbar_wait(acc_full(b), (g / TC_ACC) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TC_N);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)(c4 * 32), v);
+                    const uint32_t mask = c4 == 0 ? m0 : (c4 == 1 ? m1 : (c4 == 2 ? m2 : m3));
+                    if (live) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float s = __uint_as_float(v[c]);
+                            if (P.dbg) P.dbg[(size_t)q * P.i_pad + t0 + c4 * 32 + c] = s;
+                            if (s > thr && !((mask >> c) & 1u)) {
+                                const TcListState st = tc_insert(s, t0 + c4 * 32 + c, ls, li, n, thr, k);
+                                n = st.n; thr = st.thr;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty(b));
+            }
+            if (live) {
+                for (int s = 0; s < TC_KLIST; ++s) {
+                    P.out_ids[(size_t)q * TC_KLIST + s] = s < n ? li[s * TC_M] : -1;
+                    P.out_scores[(size_t)q * TC_KLIST + s] = s < n ? ls[s * TC_M] : 0.0f;
+                }
+                P.out_cnt[q] = n;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pack: W_h as three K-major bf16 planes [3][i_pad][64] (plane p, item j, heavy slot h) and as dense fp32 rows [n_heavy][n_items]
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void tc_pack_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
+                               const int *__restrict__ heavy_list, int n_heavy, int n_items, int i_pad,
+                               __nv_bfloat16 *__restrict__ bt, float *__restrict__ wd, int *__restrict__ neg_flag) {
+    const int h = blockIdx.y;
+    if (h >= n_heavy) return;
+    const int i = heavy_list[h];
+    const int a = wrptr[i], b = wrptr[i + 1];
+    for (int e = a + blockIdx.x * blockDim.x + threadIdx.x; e < b; e += gridDim.x * blockDim.x) {
+        const int j = wridx[e];
+        const float w = wrval[e];
+        if (w < 0.0f) *neg_flag = 1;
+        wd[(size_t)h * n_items + j] = w;
+        const __nv_bfloat16 w0 = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(w0);
+        const __nv_bfloat16 w1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 w2 = __float2bfloat16_rn(r1 - __bfloat162float(w1));
+        bt[((size_t)0 * i_pad + j) * TC_KH + h] = w0;
+        bt[((size_t)1 * i_pad + j) * TC_KH + h] = w1;
+        bt[((size_t)2 * i_pad + j) * TC_KH + h] = w2;
+    }
+}
+
+// any stored W value below zero (a light row)?  any X value below zero or not exactly a bf16?
+__global__ void tc_scan_kernel(const float *__restrict__ vals, int64_t n, int *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = vals[i];
+    if (v < 0.0f) flags[0] = 1;
+    if (__bfloat162float(__float2bfloat16_rn(v)) != v) flags[1] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// light rows + merge (CUDA cores), one CTA per query
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FX_NT = 256;
+constexpr int FX_SLOTS = 4096;
+constexpr int FX_CAP = 2560;          // light entries a user may have (table load <= 0.625)
+constexpr int FX_CAND = 1024;         // cells that can beat the tensor-core list
+constexpr double FX_SCALE = 4294967296.0;   // 2^32 fixed point
+
+struct FxShared {
+    int key[FX_SLOTS];
+    unsigned long long val[FX_SLOTS];
+    int hh[TC_KH];
+    float hx[TC_KH];
+    float cs[FX_CAND];
+    int ci[FX_CAND];
+    int n_heavy_u, n_cand, n_light, fallback;
+    float red_v[FX_NT / 32];
+    int red_i[FX_NT / 32];
+    int red_s[FX_NT / 32];
+};
+
+__device__ __forceinline__ int fx_hash(int j) { return (int)(((unsigned)j * 2654435761u) >> 20) & (FX_SLOTS - 1); }
+
+__global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
+    const int *__restrict__ rptr, const int *__restrict__ ridx, const float *__restrict__ rval, const int *__restrict__ users,
+    int n_query, const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
+    const int *__restrict__ heavy_of, const float *__restrict__ wd, int n_items, int k, int filter, int dense_mode,
+    const int *__restrict__ tc_ids, const float *__restrict__ tc_scores, const int *__restrict__ tc_cnt,
+    int *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ fallback,
+    int *__restrict__ next_query) {
+    extern __shared__ __align__(16) unsigned char fx_raw[];
+    FxShared &S = *reinterpret_cast<FxShared *>(fx_raw);
+    __shared__ int s_q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_q = atomicAdd(next_query, 1);
+        __syncthreads();
+        const int q = s_q;
+        if (q >= n_query) break;
+        const int u = users[q];
+        const int r0 = rptr[u], r1 = rptr[u + 1];
+        for (int s = tid; s < FX_SLOTS; s += FX_NT) { S.key[s] = -1; S.val[s] = 0ull; }
+        if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; }
+        __syncthreads();
+        // ---- pass 1: heavy items of the row (ascending) and the number of light entries
+        for (int base = r0; base < r1; base += FX_NT) {
+            const int p = base + tid;
+            int h = -1, cnt = 0;
+            float x = 0.f;
+            if (p < r1) {
+                const int i = ridx[p];
+                x = rval[p];
+                h = heavy_of[i];
+                if (h < 0) cnt = wrptr[i + 1] - wrptr[i];
+            }
+            // ordered compaction of the heavy items of this chunk
+            const unsigned bal = __ballot_sync(0xffffffffu, h >= 0);
+            int wsum = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+            if (lane == 0) { S.red_i[warp] = __popc(bal); S.red_s[warp] = wsum; }
+            __syncthreads();
+            int off = S.n_heavy_u, tot = 0, lsum = 0;
+            for (int w = 0; w < FX_NT / 32; ++w) { if (w < warp) off += S.red_i[w]; tot += S.red_i[w]; lsum += S.red_s[w]; }
+            if (h >= 0) { const int s = off + __popc(bal & ((1u << lane) - 1u)); if (s < TC_KH) { S.hh[s] = h; S.hx[s] = x; } }
+            __syncthreads();
+            if (tid == 0) { S.n_heavy_u += tot; S.n_light += lsum; }
+            __syncthreads();
+        }
+        if (S.n_light > FX_CAP) {      // the table would overflow: the exact kernel scores this user
+            if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
+            continue;
+        }
+        // ---- pass 2: light rows -> table (64-bit fixed-point sums: the result does not depend on the order of the adds)
+        for (int p = r0 + warp; p < r1; p += FX_NT / 32) {
+            const int i = ridx[p];
+            if (heavy_of[i] >= 0) continue;
+            const float x = rval[p];
+            for (int e = wrptr[i] + lane; e < wrptr[i + 1]; e += 32) {
+                const int j = wridx[e];
+                const float add = __fmul_rn(x, wrval[e]);
+                int slot = fx_hash(j);
+                for (;;) {
+                    const int prev = atomicCAS(&S.key[slot], -1, j);
+                    if (prev == -1 || prev == j) break;
+                    slot = (slot + 1) & (FX_SLOTS - 1);
+                }
+                atomicAdd(&S.val[slot], (unsigned long long)(long long)__double2ll_rn((double)add * FX_SCALE));
+            }
+        }
+        __syncthreads();
+        // ---- pass 3: the heavy-only list; its entries that are also table cells are superseded by the cell
+        const int n_tc = tc_cnt[q];
+        float thr = 0.0f;
+        if (tid < TC_KLIST) {
+            float s = -1.0f;
+            int j = -1;
+            if (tid < n_tc) {
+                j = tc_ids[(size_t)q * TC_KLIST + tid];
+                s = tc_scores[(size_t)q * TC_KLIST + tid];
+                int slot = fx_hash(j);
+                for (;;) {
+                    const int kk = S.key[slot];
+                    if (kk == -1) break;
+                    if (kk == j) { s = -1.0f; break; }
+                    slot = (slot + 1) & (FX_SLOTS - 1);
+                }
+            }
+            S.cs[tid] = s; S.ci[tid] = j;
+        }
+        if (tid == 0) S.n_cand = TC_KLIST;
+        __syncthreads();
+        // smallest score a cell must beat: the k-th best of the (complete) heavy-only list, 0 when the list is short
+        if (n_tc >= k) {
+            float m = 3.4e38f;
+            for (int s = 0; s < n_tc; ++s) m = fminf(m, tc_scores[(size_t)q * TC_KLIST + s]);
+            thr = m;
+        }
+        const int nh = min(S.n_heavy_u, TC_KH);
+        // ---- pass 4: every table cell: heavy part (fp32, ascending item order) + light part; interacted items drop out
+        for (int s = tid; s < FX_SLOTS; s += FX_NT) {
+            const int j = S.key[s];
+            if (j < 0) continue;
+            if (filter) {
+                int lo = r0, hi = r1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ridx[mid] < j) lo = mid + 1; else hi = mid; }
+                if (lo < r1 && ridx[lo] == j) continue;
+            }
+            float sh = 0.0f;
+            for (int e = 0; e < nh; ++e) sh = __fadd_rn(sh, __fmul_rn(S.hx[e], wd[(size_t)S.hh[e] * n_items + j]));
+            const float sc = __fadd_rn(sh, (float)((double)(long long)S.val[s] / FX_SCALE));
+            if (sc > thr || (sc == thr && sc > 0.0f)) {
+                const int c = atomicAdd(&S.n_cand, 1);
+                if (c < FX_CAND) { S.cs[c] = sc; S.ci[c] = j; }
+                else S.fallback = 1;
+            }
+        }
+        __syncthreads();
+        if (S.fallback) {
+            if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
+            continue;
+        }
+        // ---- top-k of the candidates: k rounds of arg-max, order (score desc, item id desc)
+        const int nc = S.n_cand;
+        int cnt = 0;
+        for (int round = 0; round < k; ++round) {
+            float bv = 0.0f;
+            int bi = -1, bs = -1;
+            for (int c = tid; c < nc; c += FX_NT) {
+                const float v = S.cs[c];
+                const int j = S.ci[c];
+                if (v > 0.0f && (v > bv || (v == bv && j > bi))) { bv = v; bi = j; bs = c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+                if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; bs = os; }
+            }
+            if (lane == 0) { S.red_v[warp] = bv; S.red_i[warp] = bi; S.red_s[warp] = bs; }
+            __syncthreads();
+            if (tid == 0) {
+                float v = S.red_v[0];
+                int j = S.red_i[0], sl = S.red_s[0];
+                for (int w = 1; w < FX_NT / 32; ++w)
+                    if (S.red_v[w] > v || (S.red_v[w] == v && S.red_i[w] > j)) { v = S.red_v[w]; j = S.red_i[w]; sl = S.red_s[w]; }
+                S.red_i[0] = j; S.red_v[0] = v;
+                if (j >= 0) {
+                    out_ids[(size_t)q * k + round] = j;
+                    out_scores[(size_t)q * k + round] = v;
+                    S.cs[sl] = -1.0f;
+                }
+            }
+            __syncthreads();
+            if (S.red_i[0] < 0) break;
+            ++cnt;
+            __syncthreads();
+        }
+        for (int e = cnt + tid; e < k; e += FX_NT) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+        if (tid == 0) {
+            out_cnt[q] = cnt;
+            // dense semantics list zero-score items when fewer than k are positive: the exact kernel knows that order
+            if (dense_mode && cnt < k) fallback[q] = 1;
+        }
+    }
+}
+
+typedef CUresult (*tc_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tc_encode_fn tc_encoder() {
+    static tc_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (tc_encode_fn)p;
+    }
+    return fn;
+}
+
+}  // namespace rt
+
+using namespace rt;
+
+extern "C" int rt_tc_pack_size(int32_t n_items, int32_t n_heavy, int32_t *h_i_pad, int64_t *h_bt_bytes, int64_t *h_wd_bytes) {
+    RT_ARG(n_items > 0 && n_heavy >= 0 && h_i_pad && h_bt_bytes && h_wd_bytes, "arguments");
+    const int i_pad = (n_items + TC_N - 1) / TC_N * TC_N;
+    *h_i_pad = i_pad;
+    *h_bt_bytes = (int64_t)3 * i_pad * TC_KH * 2;
+    *h_wd_bytes = (int64_t)(n_heavy > 0 ? n_heavy : 1) * n_items * 4;
+    return RT_OK;
+}
+
+extern "C" int rt_tc_pack_build(const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval, int64_t w_nnz,
+                                int32_t n_items, const int32_t *d_heavy_list, int32_t n_heavy, void *d_bt, float *d_wd,
+                                int32_t *h_w_nonneg, void *stream) {
+    RT_ARG(n_items > 0 && n_heavy >= 0 && n_heavy <= TC_KH && d_wrptr && d_bt && d_wd && h_w_nonneg, "arguments (at most 64 heavy rows)");
+    RT_ARG((((uintptr_t)d_bt) & 127) == 0, "d_bt must be 128-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t i_pad; int64_t bt_bytes, wd_bytes;
+    rt_tc_pack_size(n_items, n_heavy, &i_pad, &bt_bytes, &wd_bytes);
+    RT_CUDA(cudaMemsetAsync(d_bt, 0, (size_t)bt_bytes, st));
+    RT_CUDA(cudaMemsetAsync(d_wd, 0, (size_t)wd_bytes, st));
+    int *flags = (int *)rt::scratch(SCR_MISC, 256);
+    if (!flags) return RT_ERR_CUDA;
+    flags += 32;
+    RT_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+    if (n_heavy > 0) {
+        tc_pack_kernel<<<dim3(8, n_heavy), 256, 0, st>>>(d_wrptr, d_wridx, d_wrval, d_heavy_list, n_heavy, n_items, i_pad,
+                                                       (__nv_bfloat16 *)d_bt, d_wd, flags);
+        RT_CHECK_LAUNCH();
+    }
+    if (w_nnz > 0) {
+        tc_scan_kernel<<<(unsigned)((w_nnz + 255) / 256), 256, 0, st>>>(d_wrval, w_nnz, flags);
+        RT_CHECK_LAUNCH();
+    }
+    int h[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    *h_w_nonneg = h[0] ? 0 : 1;
+    return RT_OK;
+}
+
+extern "C" int rt_values_bf16_exact(const float *d_vals, int64_t n, int32_t *h_nonneg, int32_t *h_bf16_exact, void *stream) {
+    RT_ARG(n >= 0 && h_nonneg && h_bf16_exact && (n == 0 || d_vals), "arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *flags = (int *)rt::scratch(SCR_MISC, 256);
+    if (!flags) return RT_ERR_CUDA;
+    flags += 40;
+    RT_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
+    if (n > 0) {
+        tc_scan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_vals, n, flags);
+        RT_CHECK_LAUNCH();
+    }
+    int h[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(h, flags, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    *h_nonneg = h[0] ? 0 : 1;
+    *h_bf16_exact = h[1] ? 0 : 1;
+    return RT_OK;
+}
+
+extern "C" int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval, const int32_t *d_users,
+                                    int32_t n_query, const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval,
+                                    const int32_t *d_heavy_of, const void *d_bt, const float *d_wd, int32_t n_items, int32_t k,
+                                    int32_t filter_interacted, int32_t mode, int32_t x_planes, int32_t *d_tc_ids,
+                                    float *d_tc_scores, int32_t *d_tc_cnt, int32_t *d_out_ids, float *d_out_scores,
+                                    int32_t *d_out_cnt, int32_t *d_fallback, float *d_dbg_scores, void *stream) {
+    RT_ARG(k >= 1 && k <= TC_KLIST, "k must be in [1,16] for the tensor-core path");
+    RT_ARG(n_items > 0 && (mode == RT_TOPK_DENSE || mode == RT_TOPK_SPARSE) && (x_planes == 1 || x_planes == 3), "arguments");
+    if (n_query <= 0) return RT_OK;
+    RT_ARG(d_rptr && d_users && d_wrptr && d_heavy_of && d_bt && d_wd && d_tc_ids && d_tc_scores && d_tc_cnt && d_out_ids &&
+               d_out_scores && d_out_cnt && d_fallback, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int cc_major = 0;
+    rt_device_info(nullptr, nullptr, &cc_major, nullptr);
+    if (cc_major != 10) { rt::set_error("rt_slim_recommend_tc needs an sm_100 device (tcgen05)"); return RT_ERR_NO_DEVICE; }
+    tc_encode_fn enc = tc_encoder();
+    if (!enc) { rt::set_error("cuTensorMapEncodeTiled is not available from the driver"); return RT_ERR_CUDA; }
+    const int i_pad = (n_items + TC_N - 1) / TC_N * TC_N;
+    CUtensorMap tmap;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)TC_KH, (cuuint64_t)3 * (cuuint64_t)i_pad};
+        const cuuint64_t gstride[1] = {(cuuint64_t)TC_KH * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)TC_KH, (cuuint32_t)TC_N};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(d_bt), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { rt::set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RT_ERR_CUDA; }
+    }
+    TcParams P;
+    P.rptr = d_rptr; P.ridx = d_ridx; P.rval = d_rval; P.users = d_users; P.n_query = n_query; P.heavy_of = d_heavy_of;
+    P.n_tiles = i_pad / TC_N; P.i_pad = i_pad; P.k = k; P.filter = filter_interacted;
+    P.out_ids = d_tc_ids; P.out_scores = d_tc_scores; P.out_cnt = d_tc_cnt; P.dbg = d_dbg_scores;
+    const int n_blocks = (n_query + TC_M - 1) / TC_M;
+    int grid = rt::sm_count();
+    if (grid > n_blocks) grid = n_blocks;
+    const size_t smem = 1024 + (size_t)(x_planes + TC_STAGES * 3) * TC_TILE_BYTES + (size_t)TC_KLIST * TC_M * 8 + 16 * 8 + 64;
+    if (x_planes == 1) {
+        RT_CUDA(cudaFuncSetAttribute(recommend_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        recommend_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmap, P);
+    } else {
+        RT_CUDA(cudaFuncSetAttribute(recommend_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        recommend_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(tmap, P);
+    }
+    RT_CHECK_LAUNCH();
+    int *d_next = (int *)rt::scratch(SCR_MISC, 256);
+    if (!d_next) return RT_ERR_CUDA;
+    d_next += 48;
+    RT_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), st));
+    RT_CUDA(cudaMemsetAsync(d_fallback, 0, sizeof(int) * (size_t)n_query, st));
+    const size_t fsmem = sizeof(FxShared);
+    RT_CUDA(cudaFuncSetAttribute(recommend_tcfix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    int fgrid = rt::sm_count() * 3;
+    if (fgrid > n_query) fgrid = n_query;
+    recommend_tcfix_kernel<<<fgrid, FX_NT, fsmem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of,
+                                                      d_wd, n_items, k, filter_interacted, mode == RT_TOPK_DENSE ? 1 : 0, d_tc_ids,
+                                                      d_tc_scores, d_tc_cnt, d_out_ids, d_out_scores, d_out_cnt, d_fallback, d_next);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}

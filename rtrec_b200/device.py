@@ -325,7 +325,10 @@ def gram_cols(X: DeviceMatrix, j_begin: int = 0, j_end: Optional[int] = None, ou
 
 def set_option(name: str, value: int) -> None:
     """Tuning switches.  ``score_impl``: 3 = packed scoring kernel (default), 2 / 1 = earlier generations."""
-    global _score_impl
+    global _score_impl, _score_tc
+    if name == "score_tc":
+        _score_tc = int(value)
+        return
     if name == "score_impl":
         _score_impl = int(value)
         if int(value) == 3:
@@ -456,11 +459,107 @@ def score_pack(W: DeviceW, j_begin: int, j_end: int) -> ScorePack:
     return pack
 
 
-def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int,
-              j_begin: int = 0, j_end: Optional[int] = None):
-    """Fused scoring + filter + top-k for a batch of users (K6).  Returns device (ids, scores, cnt)."""
+@dataclass
+class TcPack:
+    """Tensor-core form of the heavy rows of W (score_tc.cu): three K-major bf16 planes + a dense fp32 copy."""
+    bt: object        # uint8 buffer [3 * i_pad * 64 * 2]
+    wd: object        # float32 [n_heavy, n_items]
+    heavy_of: object  # int32 [n_items]
+    n_heavy: int
+    w_nonneg: bool
+
+
+TC_MIN_QUERIES = 4096   # below this the exact kernel is used (a launch of the tensor-core pipeline does not pay)
+TC_KMAX = 16
+_score_tc = 1           # 0 = never use the tensor-core scoring path
+
+
+def tc_pack(W: DeviceW) -> Optional[TcPack]:
+    """Tensor-core pack of W, or None when W does not qualify (no heavy row, more than 64 heavy rows, negative weights)."""
+    if W.packs is None:
+        W.packs = {}
+    if "tc" in W.packs:
+        return W.packs["tc"]
+    t = require_cuda()
+    lib = _lib.load()
+    pk = score_pack(W, 0, W.n_items)
+    out = None
+    if 0 < pk.n_heavy <= 64:
+        i_pad, bt_b, wd_b = C.c_int32(0), C.c_int64(0), C.c_int64(0)
+        check(lib.rt_tc_pack_size(W.n_items, pk.n_heavy, C.byref(i_pad), C.byref(bt_b), C.byref(wd_b)), "rt_tc_pack_size")
+        bt = t.empty(int(bt_b.value), dtype=t.uint8, device=dev())
+        wd = t.empty(int(wd_b.value) // 4, dtype=t.float32, device=dev())
+        heavy_list = t.nonzero(pk.heavy_of >= 0).flatten().to(t.int32)   # ascending item id = heavy slot order (pack_index_kernel)
+        nonneg = C.c_int32(0)
+        check(lib.rt_tc_pack_build(ptr(W.wrptr), ptr(W.wridx), ptr(W.wrval), W.nnz, W.n_items, ptr(heavy_list), pk.n_heavy,
+                                   ptr(bt), ptr(wd), C.byref(nonneg), stream_ptr()), "rt_tc_pack_build")
+        out = TcPack(bt, wd, pk.heavy_of, pk.n_heavy, bool(nonneg.value))
+    W.packs["tc"] = out
+    return out
+
+
+def values_bf16_exact(X: DeviceMatrix) -> Tuple[bool, bool]:
+    """(all stored values of X >= 0, all exactly representable in bf16); cached on the matrix."""
+    hit = getattr(X, "_bf16_info", None)
+    if hit is None:
+        nn_, ex = C.c_int32(0), C.c_int32(0)
+        check(_lib.load().rt_values_bf16_exact(ptr(X.rval), X.nnz, C.byref(nn_), C.byref(ex), stream_ptr()), "rt_values_bf16_exact")
+        hit = (bool(nn_.value), bool(ex.value))
+        X._bf16_info = hit
+    return hit
+
+
+def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int, debug_scores: bool = False):
+    """Scoring with the heavy rows of W on the tensor cores (score_tc.cu); scores agree with the exact kernels to ~1e-6
+    relative.  Returns device (ids, scores, cnt) like ``recommend``, or None when the preconditions do not hold.  Users the
+    fast path cannot finish (light-row table overflow, dense-mode lists with fewer than k positive scores) are re-scored
+    by the exact kernel."""
     t = require_cuda()
     Q = int(users.numel())
+    if k > TC_KMAX or Q == 0:
+        return None
+    pk = tc_pack(W)
+    if pk is None or not pk.w_nonneg:
+        return None
+    x_nonneg, x_exact = values_bf16_exact(X)
+    if not x_nonneg:
+        return None
+    ids = empty(Q * k, t.int32); scores = empty(Q * k, t.float32); cnt = empty(Q, t.int32)
+    tc_ids = empty(Q * 16, t.int32); tc_sc = empty(Q * 16, t.float32); tc_cnt = empty(Q, t.int32)
+    fb = empty(Q, t.int32)
+    i_pad = (W.n_items + 127) // 128 * 128
+    dbg = t.zeros((Q, i_pad), dtype=t.float32, device=dev()) if debug_scores else None
+    check(_lib.load().rt_slim_recommend_tc(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr), ptr(W.wridx),
+                                           ptr(W.wrval), ptr(pk.heavy_of), ptr(pk.bt), ptr(pk.wd), W.n_items, int(k),
+                                           1 if filter_interacted else 0, int(mode), 1 if x_exact else 3, ptr(tc_ids), ptr(tc_sc),
+                                           ptr(tc_cnt), ptr(ids), ptr(scores), ptr(cnt), ptr(fb), ptr(dbg), stream_ptr()),
+          "rt_slim_recommend_tc")
+    ids, scores = ids.view(Q, k), scores.view(Q, k)
+    redo = t.nonzero(fb).flatten()
+    if int(redo.numel()):
+        global _score_tc
+        keep, _score_tc = _score_tc, 0
+        try:
+            r_ids, r_sc, r_cnt = recommend(X, users[redo].contiguous(), W, k, filter_interacted, mode)
+        finally:
+            _score_tc = keep
+        ids[redo] = r_ids; scores[redo] = r_sc; cnt[redo] = r_cnt
+    if debug_scores:
+        return ids, scores, cnt, dbg, (tc_ids.view(Q, 16), tc_sc.view(Q, 16), tc_cnt), redo
+    return ids, scores, cnt
+
+
+def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int,
+              j_begin: int = 0, j_end: Optional[int] = None):
+    """Fused scoring + filter + top-k for a batch of users (K6).  Returns device (ids, scores, cnt).  Large batches over the
+    whole item range go to the tensor-core path when W and X qualify (``recommend_tc``), everything else to the exact kernels."""
+    t = require_cuda()
+    Q = int(users.numel())
+    if (_score_tc and _score_impl == 3 and Q >= TC_MIN_QUERIES and k <= TC_KMAX and j_begin == 0
+            and (j_end is None or j_end == W.n_items)):
+        out = recommend_tc(X, users, W, k, filter_interacted, mode)
+        if out is not None:
+            return out
     ids = empty(max(Q * k, 1), t.int32)
     scores = empty(max(Q * k, 1), t.float32)
     cnt = empty(max(Q, 1), t.int32)

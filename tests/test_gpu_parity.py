@@ -285,6 +285,81 @@ def test_predict_family_matches_scipy(golden):
         m.predict(X.shape[0], X)
 
 
+@pytest.mark.parametrize("rating", ["half", "cont"])
+def test_tensor_core_scoring_matches_exact_scores(rating):
+    """score_tc.cu (tcgen05 + TMEM + TMA): heavy rows of W as a split-bf16 contraction, light rows and the merge on the CUDA
+    cores.  Tolerance mode (north_star: top-k equal up to score ties within tolerance): (a) every heavy-only score the
+    epilogue sees equals X_h . W_h to 5e-6 of the largest score (one bf16 plane for half-integer ratings, three for
+    continuous ones), (b) every final list is a valid top-10 of the float64 scores within 2e-5, (c) almost all lists are
+    identical to the exact kernel's."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200._lib import RT_TOPK_DENSE, RT_TOPK_SPARSE
+    rng = np.random.default_rng(23)
+    n_items, n_users = 3000, 5000
+    rows, cols, vals = [], [], []
+    heavy = np.sort(rng.choice(n_items, 40, replace=False))
+    for i in heavy:
+        c = np.flatnonzero(rng.random(n_items) < 0.3)
+        rows.append(np.full(len(c), i)); cols.append(c); vals.append((rng.random(len(c)) * 0.3).astype(np.float32))
+    nb = 4 * n_items
+    rows.append(rng.integers(0, n_items, nb)); cols.append(rng.integers(0, n_items, nb)); vals.append((rng.random(nb) * 0.2).astype(np.float32))
+    W = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n_items, n_items))
+    W.sum_duplicates()
+    xr, xc = [], []
+    for u in range(n_users):
+        its = np.unique(np.concatenate([rng.choice(n_items, int(rng.integers(1, 80)), replace=False),
+                                        rng.choice(heavy, int(rng.integers(0, 12)), replace=False)]))
+        xr.append(np.full(len(its), u)); xc.append(its)
+    xr, xc = np.concatenate(xr), np.concatenate(xc)
+    xv = (rng.integers(1, 11, len(xr)) * 0.5 if rating == "half" else rng.uniform(0.05, 5.0, len(xr))).astype(np.float32)
+    X = sp.csr_matrix((xv, (xr, xc)), shape=(n_users, n_items))
+    dX, dW = D.DeviceMatrix.from_scipy(X), D.DeviceW.from_scipy(W)
+    users = torch.from_numpy(rng.permutation(n_users).astype(np.int32)).cuda()
+    uh = users.cpu().numpy()
+    old_min = D.PACK_MIN_ROW
+    try:
+        D.PACK_MIN_ROW = 256
+        pk = D.tc_pack(dW)
+        assert pk is not None and pk.n_heavy == 40 and pk.w_nonneg
+        assert D.values_bf16_exact(dX) == (True, rating == "half")
+        S64 = np.asarray((X.astype(np.float64) @ W.astype(np.float64)).todense())
+        Wr = W.tocsr()
+        hmask = np.zeros(n_items, bool); hmask[heavy] = True
+        Xh = X.copy().tocsc(); Xh.data[~hmask[np.repeat(np.arange(n_items), np.diff(Xh.indptr))]] = 0
+        Sh64 = np.asarray((Xh.tocsr().astype(np.float64) @ W.astype(np.float64)).todense())
+        for mode in (RT_TOPK_SPARSE, RT_TOPK_DENSE):
+            for filt in (True, False):
+                ids, sc, cnt, dbg, tc, redo = D.recommend_tc(dX, users, dW, 10, filt, mode, debug_scores=True)
+                dbg = dbg.cpu().numpy()[:, :n_items]
+                scale = float(Sh64.max())
+                err = np.abs(dbg - Sh64[uh]).max()
+                assert err <= 5e-6 * scale, (rating, mode, filt, err, scale)
+                ids, sc, cnt = ids.cpu().numpy(), sc.cpu().numpy(), cnt.cpu().numpy()
+                D.set_option("score_tc", 0)
+                e_ids, e_sc, e_cnt = [x.cpu().numpy() for x in D.recommend(dX, users, dW, 10, filt, mode)]
+                D.set_option("score_tc", 1)
+                assert np.array_equal(cnt, e_cnt)
+                same = 0
+                for q in range(n_users):
+                    u = int(uh[q])
+                    inter = np.zeros(n_items, bool)
+                    if filt:
+                        inter[X[u].indices] = True
+                    elig = ~inter if mode == RT_TOPK_DENSE else (~inter & (S64[u] != 0))
+                    ok, why = topk_consistent(ids[q, :cnt[q]].tolist(), S64[u], 10, elig, tol=2e-5)
+                    assert ok, (rating, mode, filt, q, why)
+                    same += int(np.array_equal(ids[q], e_ids[q]))
+                assert same >= 0.98 * n_users, (same, n_users)
+                assert int(redo.numel()) < 0.2 * n_users
+        # the public entry point takes this path for large batches by itself
+        a = D.recommend(dX, users, dW, 10, True, RT_TOPK_SPARSE)
+        assert a[0].shape == (n_users, 10)
+    finally:
+        D.PACK_MIN_ROW = old_min
+        D.set_option("score_tc", 1)
+
+
 @pytest.mark.parametrize("nn", [20, None])
 def test_trivial_columns_shortcut_gives_the_same_w(nn):
     """Targets whose Gram row has no entry above the L1 threshold are zero before the first sweep.  Bulk fits return them
