@@ -406,12 +406,13 @@ int rt_slim_similar(const int32_t *d_wptr, const int32_t *d_widx, const float *d
  * of W and of X is >= 0 (a light contribution can then only raise a score), at most 64 heavy rows.
  *   rt_tc_pack_size / rt_tc_pack_build: per W, the heavy rows (d_heavy_list[n_heavy], ascending item id = heavy slot, as
  *     rt_w_pack_plan numbers them) as three K-major bf16 planes d_bt[3][i_pad][64] (w = w0 + w1 + w2; TMA source, 128-byte
- *     aligned) and as dense fp32 rows d_wd[n_heavy][n_items]; *h_w_nonneg = 1 iff no stored value of W is negative.
+ *     aligned) and as dense fp32 rows d_wd[n_heavy + 1][n_items] (the last row = column maxima over the heavy rows, the bound
+ *     that lets the merge kernel drop most light cells after one load); *h_w_nonneg = 1 iff no stored value of W is negative.
  *     Synchronises.
  *   rt_values_bf16_exact: are all n values >= 0 / exactly representable in bf16 (integer and half-integer ratings are:
  *     one operand plane instead of three).  Synchronises.
- *   rt_slim_recommend_tc: x_planes = 1 or 3 (see above); d_tc_* [n_query, 16] / [n_query] receive the heavy-only candidate
- *     lists of the tensor-core kernel, d_out_* the final lists (as rt_slim_recommend_packed), d_fallback[n_query] != 0
+ *   rt_slim_recommend_tc: x_planes = 1 or 3 (see above); d_tc_* [n_query, 32] / [n_query] receive the heavy-only candidate
+ *     lists of the tensor-core kernel (two lists of <= k per query, one per column half of the accumulators, -1 padded), d_out_* the final lists (as rt_slim_recommend_packed), d_fallback[n_query] != 0
  *     marks queries the fast path could not finish (the caller re-scores them with rt_slim_recommend_packed);
  *     d_dbg_scores (optional, [n_query, i_pad]) receives every heavy-only score (tests).  Needs an sm_100 device.
  */
@@ -422,8 +423,8 @@ int rt_tc_pack_build(const int32_t *d_wrptr, const int32_t *d_wridx, const float
 int rt_values_bf16_exact(const float *d_vals, int64_t n, int32_t *h_nonneg, int32_t *h_bf16_exact, void *stream);
 int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval, const int32_t *d_users,
                          int32_t n_query, const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval,
-                         const int32_t *d_heavy_of, const void *d_bt, const float *d_wd, int32_t n_items, int32_t k,
-                         int32_t filter_interacted, int32_t mode, int32_t x_planes, int32_t *d_tc_ids,
+                         const int32_t *d_heavy_of, int32_t n_heavy, const void *d_bt, const float *d_wd, int32_t n_items,
+                         int32_t k, int32_t filter_interacted, int32_t mode, int32_t x_planes, int32_t *d_tc_ids,
                          float *d_tc_scores, int32_t *d_tc_cnt, int32_t *d_out_ids, float *d_out_scores,
                          int32_t *d_out_cnt, int32_t *d_fallback, float *d_dbg_scores, void *stream);
 

@@ -96,8 +96,8 @@ PROTOTYPES = {
     "rt_tc_pack_size": (C.c_int, [_I32, _I32, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64)]),
     "rt_tc_pack_build": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _I32, _P, _P, C.POINTER(_I32), _P]),
     "rt_values_bf16_exact": (C.c_int, [_P, _I64, C.POINTER(_I32), C.POINTER(_I32), _P]),
-    "rt_slim_recommend_tc": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P,
-                                       _P, _P, _P, _P, _P, _P]),
+    "rt_slim_recommend_tc": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P,
+                                       _P, _P, _P, _P, _P, _P, _P]),
     "rt_lru_replay": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, C.POINTER(_I64)]),
     "rt_eval_metrics": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _P]),
     "rt_set_option": (C.c_int, [C.c_char_p, _I32]),

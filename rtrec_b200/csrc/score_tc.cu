@@ -38,7 +38,9 @@ constexpr int TC_KH = 64;        // heavy rows (K of one operand tile: 64 bf16 =
 constexpr int TC_STAGES = 3;     // W_h ring
 constexpr int TC_ACC = 4;        // TMEM accumulator buffers (4 x 128 = 512 columns)
 constexpr int TC_KLIST = 16;     // longest list kept per user
-constexpr int TC_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: operand gather + epilogue
+constexpr int TC_EPI_WARPS = 8;  // two warps per TMEM lane quadrant: each takes half of the columns of every accumulator
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: operand gather + epilogue
+constexpr int TC_OUT = 2 * TC_KLIST;   // candidates written per user (one list per column half)
 constexpr int TC_TILE_BYTES = TC_N * TC_KH * 2;   // one [128 rows x 64 bf16] operand tile
 
 struct TcParams {
@@ -49,7 +51,7 @@ struct TcParams {
     const int *heavy_of;     // item -> heavy slot (< TC_KH) or -1
     int n_tiles, i_pad;      // item tiles of TC_N, padded item count
     int k, filter;
-    int *out_ids;            // [n_query, TC_KLIST] heavy-only candidates (unsorted)
+    int *out_ids;            // [n_query, TC_OUT] heavy-only candidates (two unsorted lists of <= k, -1 padded)
     float *out_scores;
     int *out_cnt;
     float *dbg;              // optional [n_query, i_pad]: every heavy-only score (tests)
@@ -135,6 +137,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return r;
+}
+
 // byte offset of element (row, k) inside a swizzled operand tile (Swizzle<3,4,3>: 16-byte chunk index ^= row % 8)
 __device__ __forceinline__ int tc_sw_off(int row, int k) {
     const int chunk = (k >> 3) ^ (row & 7);
@@ -166,9 +175,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
     unsigned char *smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     unsigned char *sA = smem;                                         // SX tiles
     unsigned char *sB = sA + SX * TC_TILE_BYTES;                      // TC_STAGES x 3 tiles
-    float *list_s = reinterpret_cast<float *>(sB + TC_STAGES * 3 * TC_TILE_BYTES);
-    int *list_i = reinterpret_cast<int *>(list_s + TC_KLIST * TC_M);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(list_i + TC_KLIST * TC_M);
+    float *list_s = reinterpret_cast<float *>(sB + TC_STAGES * 3 * TC_TILE_BYTES);   // [half][slot][row]
+    int *list_i = reinterpret_cast<int *>(list_s + 2 * TC_KLIST * TC_M);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(list_i + 2 * TC_KLIST * TC_M);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
     const uint32_t bar0 = smem_u32(bars);
     auto b_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -180,8 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int b = 0; b < TC_ACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
-        mbar_init(a_full, 4);
+        for (int b = 0; b < TC_ACC; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), TC_EPI_WARPS); }
+        mbar_init(a_full, TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -240,12 +249,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
                 }
             }
         } else {
-            // ===== operand gather + epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = users of those rows
+            // ===== operand gather + epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = users of those rows; the two warps of a
+            // quadrant split the columns of every accumulator (half 0: columns 0-63, half 1: 64-127)
             const int quad = warp & 3;
+            const int half = (warp - 2) >> 2;
             const int row = quad * 32 + lane;
             // ---- X_h of the 128 users -> swizzled A tile(s): one user at a time per warp, lanes stride over its CSR row
-            for (int uu = 0; uu < 32; ++uu) {
-                const int r = quad * 32 + uu;
+            for (int uu = 0; uu < 16; ++uu) {
+                const int r = quad * 32 + half * 16 + uu;
                 const int q = blk * TC_M + r;
                 if (lane < 8) {
 #pragma unroll
@@ -278,44 +289,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
 
-            // ---- epilogue
+            // ---- epilogue.  One warp per scheduler has little latency hiding, so the common case is kept to a handful of
+            // instructions per 32 columns: the maximum of the chunk (FMNMX3 tree) against the user's threshold; only chunks in
+            // which some lane has a candidate build the per-lane pass mask, and the candidates themselves are re-read from TMEM
+            // one column at a time (warp-uniform loop over the union of the pass masks), because registers cannot be indexed
+            // by a run-time column.
             const int q = blk * TC_M + row;
             const bool live = q < P.n_query;
             int r_cur = 0, r_end = 0;
             if (live && P.filter) { const int u = P.users[q]; r_cur = P.rptr[u]; r_end = P.rptr[u + 1]; }
-            float *ls = list_s + row;
-            int *li = list_i + row;
+            int nxt = r_cur < r_end ? P.ridx[r_cur] : 0x7fffffff;     // next interacted item of this user
+            float *ls = list_s + half * TC_KLIST * TC_M + row;
+            int *li = list_i + half * TC_KLIST * TC_M + row;
             int n = 0;
             float thr = 0.0f;    // scores are >= 0 (W >= 0, X >= 0): only positive ones are candidates
             const int k = P.k;
             for (int t = 0; t < NT; ++t) {
                 const int g = it * NT + t, b = g % TC_ACC;
                 const int t0 = t * TC_N;
-                // interacted items of this tile as a 128-bit mask (the row is ascending: a cursor walks it once per block)
-                uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                while (r_cur < r_end) {
-                    const int c = P.ridx[r_cur] - t0;
-                    if (c >= TC_N) break;
+                // interacted items of this tile (own half) as two 32-bit masks; the row is ascending: a cursor walks it once
+                uint32_t ma = 0, mb = 0;
+                while (nxt < t0 + TC_N) {
+                    const int c = nxt - t0 - half * 64;
                     const uint32_t bit = 1u << (c & 31);
-                    const int w = c >> 5;
-                    m0 |= w == 0 ? bit : 0u; m1 |= w == 1 ? bit : 0u; m2 |= w == 2 ? bit : 0u; m3 |= w == 3 ? bit : 0u;
+                    ma |= (c >> 5) == 0 ? bit : 0u; mb |= (c >> 5) == 1 ? bit : 0u;
                     ++r_cur;
+                    nxt = r_cur < r_end ? P.ridx[r_cur] : 0x7fffffff;
                 }
                 mbar_wait(acc_full(b), (g / TC_ACC) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TC_N);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TC_N + half * 64);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
+                for (int cc = 0; cc < 2; ++cc) {
                     uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)(c4 * 32), v);
-                    const uint32_t mask = c4 == 0 ? m0 : (c4 == 1 ? m1 : (c4 == 2 ? m2 : m3));
-                    if (live) {
+                    tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+                    const int col0 = t0 + half * 64 + cc * 32;
+                    if (P.dbg && live) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float s = __uint_as_float(v[c]);
-                            if (P.dbg) P.dbg[(size_t)q * P.i_pad + t0 + c4 * 32 + c] = s;
-                            if (s > thr && !((mask >> c) & 1u)) {
-                                const TcListState st = tc_insert(s, t0 + c4 * 32 + c, ls, li, n, thr, k);
+                        for (int c = 0; c < 32; ++c) P.dbg[(size_t)q * P.i_pad + col0 + c] = __uint_as_float(v[c]);
+                    }
+                    float mx = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int c = 1; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+                    if (__any_sync(0xffffffffu, live && mx > thr)) {
+                        uint32_t pm = 0;
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) pm |= (__uint_as_float(v[c]) > thr) ? (1u << c) : 0u;
+                        pm &= ~(cc == 0 ? ma : mb);
+                        if (!live) pm = 0;
+                        uint32_t un = __reduce_or_sync(0xffffffffu, pm);
+                        while (un) {
+                            const int c = __ffs(un) - 1;
+                            un &= un - 1;
+                            const float sv = __uint_as_float(tmem_ld1(taddr + (uint32_t)(cc * 32 + c)));
+                            if (((pm >> c) & 1u) && sv > thr) {
+                                const TcListState st = tc_insert(sv, col0 + c, ls, li, n, thr, k);
                                 n = st.n; thr = st.thr;
                             }
                         }
@@ -327,10 +355,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
             }
             if (live) {
                 for (int s = 0; s < TC_KLIST; ++s) {
-                    P.out_ids[(size_t)q * TC_KLIST + s] = s < n ? li[s * TC_M] : -1;
-                    P.out_scores[(size_t)q * TC_KLIST + s] = s < n ? ls[s * TC_M] : 0.0f;
+                    P.out_ids[(size_t)q * TC_OUT + half * TC_KLIST + s] = s < n ? li[s * TC_M] : -1;
+                    P.out_scores[(size_t)q * TC_OUT + half * TC_KLIST + s] = s < n ? ls[s * TC_M] : 0.0f;
                 }
-                P.out_cnt[q] = n;
+                if (half == 0) P.out_cnt[q] = 0;   // (the lists carry -1 padding; the count is kept for the interface)
             }
         }
     }
@@ -346,7 +374,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
                                const int *__restrict__ heavy_list, int n_heavy, int n_items, int i_pad,
-                               __nv_bfloat16 *__restrict__ bt, float *__restrict__ wd, int *__restrict__ neg_flag) {
+                               __nv_bfloat16 *__restrict__ bt, float *__restrict__ wd, float *__restrict__ colmax,
+                               int *__restrict__ neg_flag) {
     const int h = blockIdx.y;
     if (h >= n_heavy) return;
     const int i = heavy_list[h];
@@ -356,6 +385,7 @@ __global__ void tc_pack_kernel(const int *__restrict__ wrptr, const int *__restr
         const float w = wrval[e];
         if (w < 0.0f) *neg_flag = 1;
         wd[(size_t)h * n_items + j] = w;
+        if (w > 0.0f) atomicMax(reinterpret_cast<int *>(colmax + j), __float_as_int(w));   // non-negative floats order like ints
         const __nv_bfloat16 w0 = __float2bfloat16_rn(w);
         const float r1 = w - __bfloat162float(w0);
         const __nv_bfloat16 w1 = __float2bfloat16_rn(r1);
@@ -381,18 +411,24 @@ __global__ void tc_scan_kernel(const float *__restrict__ vals, int64_t n, int *_
 constexpr int FX_NT = 256;
 constexpr int FX_SLOTS = 4096;
 constexpr int FX_CAP = 2560;          // light entries a user may have (table load <= 0.625)
-constexpr int FX_CAND = 1024;         // cells that can beat the tensor-core list
+constexpr int FX_CAND = 64;           // candidates kept for the final selection (tensor-core lists + surviving cells)
 constexpr double FX_SCALE = 4294967296.0;   // 2^32 fixed point
 
+constexpr int FX_ROWS = 1024;         // light items of one user's row that can be staged
+
 struct FxShared {
-    int key[FX_SLOTS];
     unsigned long long val[FX_SLOTS];
+    int key[FX_SLOTS];
+    int la[FX_ROWS];     // staged light rows: first entry in W's CSR, exclusive prefix of the lengths, rating
+    int lpre[FX_ROWS + 1];
+    float lx[FX_ROWS];
+    int n_rows;
     int hh[TC_KH];
     float hx[TC_KH];
     float cs[FX_CAND];
     int ci[FX_CAND];
     int n_heavy_u, n_cand, n_light, fallback;
-    float red_v[FX_NT / 32];
+    float thr, x1;
     int red_i[FX_NT / 32];
     int red_s[FX_NT / 32];
 };
@@ -402,8 +438,8 @@ __device__ __forceinline__ int fx_hash(int j) { return (int)(((unsigned)j * 2654
 __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
     const int *__restrict__ rptr, const int *__restrict__ ridx, const float *__restrict__ rval, const int *__restrict__ users,
     int n_query, const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
-    const int *__restrict__ heavy_of, const float *__restrict__ wd, int n_items, int k, int filter, int dense_mode,
-    const int *__restrict__ tc_ids, const float *__restrict__ tc_scores, const int *__restrict__ tc_cnt,
+    const int *__restrict__ heavy_of, const float *__restrict__ wd, const float *__restrict__ colmax, int n_items, int k,
+    int filter, int dense_mode, const int *__restrict__ tc_ids, const float *__restrict__ tc_scores,
     int *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ fallback,
     int *__restrict__ next_query) {
     extern __shared__ __align__(16) unsigned char fx_raw[];
@@ -418,96 +454,139 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
         if (q >= n_query) break;
         const int u = users[q];
         const int r0 = rptr[u], r1 = rptr[u + 1];
-        for (int s = tid; s < FX_SLOTS; s += FX_NT) { S.key[s] = -1; S.val[s] = 0ull; }
-        if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; }
+        {   // clear the table with 16-byte stores
+            uint4 *kv = reinterpret_cast<uint4 *>(S.key);
+            uint4 *vv = reinterpret_cast<uint4 *>(S.val);
+            for (int s = tid; s < FX_SLOTS / 4; s += FX_NT) kv[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            for (int s = tid; s < FX_SLOTS / 2; s += FX_NT) vv[s] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; S.n_rows = 0; }
         __syncthreads();
-        // ---- pass 1: heavy items of the row (ascending) and the number of light entries
+        // ---- pass 1: one coalesced sweep over the row: heavy items (ascending, ordered compaction) and the light rows
+        // (first entry, length, rating) staged in shared memory -- the scatter below then has no dependent global loads
         for (int base = r0; base < r1; base += FX_NT) {
             const int p = base + tid;
-            int h = -1, cnt = 0;
+            int h = -1, a = 0, len = 0;
             float x = 0.f;
             if (p < r1) {
                 const int i = ridx[p];
                 x = rval[p];
                 h = heavy_of[i];
-                if (h < 0) cnt = wrptr[i + 1] - wrptr[i];
+                if (h < 0) { a = wrptr[i]; len = wrptr[i + 1] - a; }
             }
-            // ordered compaction of the heavy items of this chunk
+            if (len > 0) {
+                const int slot = atomicAdd(&S.n_rows, 1);
+                if (slot < FX_ROWS) { S.la[slot] = a; S.lpre[slot] = len; S.lx[slot] = x; }
+            }
             const unsigned bal = __ballot_sync(0xffffffffu, h >= 0);
-            int wsum = cnt;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-            if (lane == 0) { S.red_i[warp] = __popc(bal); S.red_s[warp] = wsum; }
+            if (lane == 0) S.red_i[warp] = __popc(bal);
             __syncthreads();
-            int off = S.n_heavy_u, tot = 0, lsum = 0;
-            for (int w = 0; w < FX_NT / 32; ++w) { if (w < warp) off += S.red_i[w]; tot += S.red_i[w]; lsum += S.red_s[w]; }
+            int off = S.n_heavy_u, tot = 0;
+            for (int w = 0; w < FX_NT / 32; ++w) { if (w < warp) off += S.red_i[w]; tot += S.red_i[w]; }
             if (h >= 0) { const int s = off + __popc(bal & ((1u << lane) - 1u)); if (s < TC_KH) { S.hh[s] = h; S.hx[s] = x; } }
             __syncthreads();
-            if (tid == 0) { S.n_heavy_u += tot; S.n_light += lsum; }
+            if (tid == 0) S.n_heavy_u += tot;
             __syncthreads();
         }
-        if (S.n_light > FX_CAP) {      // the table would overflow: the exact kernel scores this user
+        const int n_rows = S.n_rows;
+        if (n_rows > FX_ROWS) {         // more light items than can be staged: the exact kernel scores this user
             if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
             continue;
         }
-        // ---- pass 2: light rows -> table (64-bit fixed-point sums: the result does not depend on the order of the adds)
-        for (int p = r0 + warp; p < r1; p += FX_NT / 32) {
-            const int i = ridx[p];
-            if (heavy_of[i] >= 0) continue;
-            const float x = rval[p];
-            for (int e = wrptr[i] + lane; e < wrptr[i + 1]; e += 32) {
-                const int j = wridx[e];
-                const float add = __fmul_rn(x, wrval[e]);
-                int slot = fx_hash(j);
-                for (;;) {
-                    const int prev = atomicCAS(&S.key[slot], -1, j);
-                    if (prev == -1 || prev == j) break;
-                    slot = (slot + 1) & (FX_SLOTS - 1);
-                }
-                atomicAdd(&S.val[slot], (unsigned long long)(long long)__double2ll_rn((double)add * FX_SCALE));
+        // exclusive prefix of the staged lengths (one warp, 32 rows per step)
+        if (warp == 0) {
+            int run = 0;
+            for (int b0 = 0; b0 < n_rows; b0 += 32) {
+                const int r = b0 + lane;
+                const int len = r < n_rows ? S.lpre[r] : 0;
+                int inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t_; }
+                if (r < n_rows) S.lpre[r] = run + inc - len;
+                run += __shfl_sync(0xffffffffu, inc, 31);
             }
+            if (lane == 0) { S.lpre[n_rows] = run; S.n_light = run; }
         }
         __syncthreads();
-        // ---- pass 3: the heavy-only list; its entries that are also table cells are superseded by the cell
-        const int n_tc = tc_cnt[q];
-        float thr = 0.0f;
-        if (tid < TC_KLIST) {
-            float s = -1.0f;
-            int j = -1;
-            if (tid < n_tc) {
-                j = tc_ids[(size_t)q * TC_KLIST + tid];
-                s = tc_scores[(size_t)q * TC_KLIST + tid];
-                int slot = fx_hash(j);
-                for (;;) {
-                    const int kk = S.key[slot];
-                    if (kk == -1) break;
-                    if (kk == j) { s = -1.0f; break; }
-                    slot = (slot + 1) & (FX_SLOTS - 1);
-                }
-            }
-            S.cs[tid] = s; S.ci[tid] = j;
-        }
-        if (tid == 0) S.n_cand = TC_KLIST;
-        __syncthreads();
-        // smallest score a cell must beat: the k-th best of the (complete) heavy-only list, 0 when the list is short
-        if (n_tc >= k) {
-            float m = 3.4e38f;
-            for (int s = 0; s < n_tc; ++s) m = fminf(m, tc_scores[(size_t)q * TC_KLIST + s]);
-            thr = m;
+        const int n_light = S.n_light;
+        if (n_light > FX_CAP) {      // the table would overflow: the exact kernel scores this user
+            if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
+            continue;
         }
         const int nh = min(S.n_heavy_u, TC_KH);
-        // ---- pass 4: every table cell: heavy part (fp32, ascending item order) + light part; interacted items drop out
+        // ---- pass 2: every light entry -> table, one entry per thread and step (64-bit fixed-point sums: the result does
+        // not depend on the order of the adds)
+        for (int e = tid; e < n_light; e += FX_NT) {
+            int lo = 0, hi = n_rows;            // staged row of entry e: last r with lpre[r] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.lpre[mid] <= e) lo = mid; else hi = mid; }
+            const int ge = S.la[lo] + (e - S.lpre[lo]);
+            const int j = wridx[ge];
+            const float add = __fmul_rn(S.lx[lo], wrval[ge]);
+            int slot = fx_hash(j);
+            for (;;) {
+                const int prev = atomicCAS(&S.key[slot], -1, j);
+                if (prev == -1 || prev == j) break;
+                slot = (slot + 1) & (FX_SLOTS - 1);
+            }
+            atomicAdd(&S.val[slot], (unsigned long long)__double2ll_rn((double)add * FX_SCALE));
+        }
+        // ---- pass 3 (warp 0, meanwhile): the two heavy-only lists of the tensor-core kernel -> candidates 0..31; the
+        // smallest score a cell must beat = k-th best of their union (0 while the union is short); sum of the heavy ratings
+        if (warp == 0) {
+            const int j = tc_ids[(size_t)q * TC_OUT + lane];
+            const float sc = j >= 0 ? tc_scores[(size_t)q * TC_OUT + lane] : -1.0f;
+            S.cs[lane] = sc; S.ci[lane] = j;
+            int rank = 0;       // entries strictly better than mine (ties by lane)
+            for (int l = 0; l < 32; ++l) {
+                const float o = __shfl_sync(0xffffffffu, sc, l);
+                rank += (o > sc) || (o == sc && l < lane);
+            }
+            const unsigned has = __ballot_sync(0xffffffffu, j >= 0);
+            float thr = 0.0f;
+            const unsigned kth = __ballot_sync(0xffffffffu, rank == k - 1 && j >= 0);
+            if (__popc(has) >= k && kth) thr = __shfl_sync(0xffffffffu, sc, __ffs(kth) - 1);
+            float x1 = 0.0f;
+            for (int e = lane; e < nh; e += 32) x1 += S.hx[e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+            if (lane == 0) { S.thr = thr; S.x1 = x1; S.n_cand = 32; }
+        }
+        __syncthreads();
+        const float thr = S.thr, x1 = S.x1;
+        // tensor-core candidates that are also table cells are superseded by the cell (which carries the light part)
+        if (tid < 32 && S.ci[tid] >= 0) {
+            const int j = S.ci[tid];
+            int slot = fx_hash(j);
+            for (;;) {
+                const int kk = S.key[slot];
+                if (kk == -1) break;
+                if (kk == j) { S.cs[tid] = -1.0f; break; }
+                slot = (slot + 1) & (FX_SLOTS - 1);
+            }
+        }
+        // ---- pass 4: table cells.  Heavy part <= x1 * colmax[j] (every term is >= 0): most cells cannot reach the threshold
+        // and are dropped after one load; the others get their heavy part (fp32, ascending item order) from the dense rows
         for (int s = tid; s < FX_SLOTS; s += FX_NT) {
             const int j = S.key[s];
             if (j < 0) continue;
+            const float lpart = (float)((double)(long long)S.val[s] / FX_SCALE);
+            const float bound = __fadd_rn(lpart, __fmul_rn(__fmul_rn(x1, colmax[j]), 1.00001f));
+            if (bound < thr) continue;
             if (filter) {
                 int lo = r0, hi = r1;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (ridx[mid] < j) lo = mid + 1; else hi = mid; }
                 if (lo < r1 && ridx[lo] == j) continue;
             }
             float sh = 0.0f;
-            for (int e = 0; e < nh; ++e) sh = __fadd_rn(sh, __fmul_rn(S.hx[e], wd[(size_t)S.hh[e] * n_items + j]));
-            const float sc = __fadd_rn(sh, (float)((double)(long long)S.val[s] / FX_SCALE));
+            int e = 0;
+            for (; e + 3 < nh; e += 4) {       // four gathers in flight, added in ascending item order
+                const float g0 = wd[(size_t)S.hh[e] * n_items + j], g1 = wd[(size_t)S.hh[e + 1] * n_items + j];
+                const float g2 = wd[(size_t)S.hh[e + 2] * n_items + j], g3 = wd[(size_t)S.hh[e + 3] * n_items + j];
+                sh = __fadd_rn(sh, __fmul_rn(S.hx[e], g0)); sh = __fadd_rn(sh, __fmul_rn(S.hx[e + 1], g1));
+                sh = __fadd_rn(sh, __fmul_rn(S.hx[e + 2], g2)); sh = __fadd_rn(sh, __fmul_rn(S.hx[e + 3], g3));
+            }
+            for (; e < nh; ++e) sh = __fadd_rn(sh, __fmul_rn(S.hx[e], wd[(size_t)S.hh[e] * n_items + j]));
+            const float sc = __fadd_rn(sh, lpart);
             if (sc > thr || (sc == thr && sc > 0.0f)) {
                 const int c = atomicAdd(&S.n_cand, 1);
                 if (c < FX_CAND) { S.cs[c] = sc; S.ci[c] = j; }
@@ -519,48 +598,28 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
             if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
             continue;
         }
-        // ---- top-k of the candidates: k rounds of arg-max, order (score desc, item id desc)
-        const int nc = S.n_cand;
-        int cnt = 0;
-        for (int round = 0; round < k; ++round) {
-            float bv = 0.0f;
-            int bi = -1, bs = -1;
-            for (int c = tid; c < nc; c += FX_NT) {
-                const float v = S.cs[c];
-                const int j = S.ci[c];
-                if (v > 0.0f && (v > bv || (v == bv && j > bi))) { bv = v; bi = j; bs = c; }
+        // ---- top-k of the (<= 64) candidates by one warp: rank by (score desc, item id desc), positive scores only
+        if (warp == 0) {
+            const int nc = min(S.n_cand, FX_CAND);
+            float v0 = lane < nc ? S.cs[lane] : -1.0f, v1 = lane + 32 < nc ? S.cs[lane + 32] : -1.0f;
+            int j0 = lane < nc ? S.ci[lane] : -1, j1 = lane + 32 < nc ? S.ci[lane + 32] : -1;
+            int rk0 = 0, rk1 = 0;
+            for (int l = 0; l < 32; ++l) {
+                const float a0 = __shfl_sync(0xffffffffu, v0, l), a1 = __shfl_sync(0xffffffffu, v1, l);
+                const int b0 = __shfl_sync(0xffffffffu, j0, l), b1 = __shfl_sync(0xffffffffu, j1, l);
+                rk0 += (a0 > v0 || (a0 == v0 && b0 > j0)) + (a1 > v0 || (a1 == v0 && b1 > j0));
+                rk1 += (a0 > v1 || (a0 == v1 && b0 > j1)) + (a1 > v1 || (a1 == v1 && b1 > j1));
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; bs = os; }
+            const bool ok0 = v0 > 0.0f && rk0 < k, ok1 = v1 > 0.0f && rk1 < k;
+            if (ok0) { out_ids[(size_t)q * k + rk0] = j0; out_scores[(size_t)q * k + rk0] = v0; }
+            if (ok1) { out_ids[(size_t)q * k + rk1] = j1; out_scores[(size_t)q * k + rk1] = v1; }
+            const int cnt = __popc(__ballot_sync(0xffffffffu, ok0)) + __popc(__ballot_sync(0xffffffffu, ok1));
+            for (int e = cnt + lane; e < k; e += 32) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+            if (lane == 0) {
+                out_cnt[q] = cnt;
+                // dense semantics list zero-score items when fewer than k are positive: the exact kernel knows that order
+                if (dense_mode && cnt < k) fallback[q] = 1;
             }
-            if (lane == 0) { S.red_v[warp] = bv; S.red_i[warp] = bi; S.red_s[warp] = bs; }
-            __syncthreads();
-            if (tid == 0) {
-                float v = S.red_v[0];
-                int j = S.red_i[0], sl = S.red_s[0];
-                for (int w = 1; w < FX_NT / 32; ++w)
-                    if (S.red_v[w] > v || (S.red_v[w] == v && S.red_i[w] > j)) { v = S.red_v[w]; j = S.red_i[w]; sl = S.red_s[w]; }
-                S.red_i[0] = j; S.red_v[0] = v;
-                if (j >= 0) {
-                    out_ids[(size_t)q * k + round] = j;
-                    out_scores[(size_t)q * k + round] = v;
-                    S.cs[sl] = -1.0f;
-                }
-            }
-            __syncthreads();
-            if (S.red_i[0] < 0) break;
-            ++cnt;
-            __syncthreads();
-        }
-        for (int e = cnt + tid; e < k; e += FX_NT) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
-        if (tid == 0) {
-            out_cnt[q] = cnt;
-            // dense semantics list zero-score items when fewer than k are positive: the exact kernel knows that order
-            if (dense_mode && cnt < k) fallback[q] = 1;
         }
     }
 }
@@ -590,7 +649,7 @@ extern "C" int rt_tc_pack_size(int32_t n_items, int32_t n_heavy, int32_t *h_i_pa
     const int i_pad = (n_items + TC_N - 1) / TC_N * TC_N;
     *h_i_pad = i_pad;
     *h_bt_bytes = (int64_t)3 * i_pad * TC_KH * 2;
-    *h_wd_bytes = (int64_t)(n_heavy > 0 ? n_heavy : 1) * n_items * 4;
+    *h_wd_bytes = (int64_t)((n_heavy > 0 ? n_heavy : 1) + 1) * n_items * 4;   // dense rows + one row of column maxima
     return RT_OK;
 }
 
@@ -610,7 +669,7 @@ extern "C" int rt_tc_pack_build(const int32_t *d_wrptr, const int32_t *d_wridx, 
     RT_CUDA(cudaMemsetAsync(flags, 0, 2 * sizeof(int), st));
     if (n_heavy > 0) {
         tc_pack_kernel<<<dim3(8, n_heavy), 256, 0, st>>>(d_wrptr, d_wridx, d_wrval, d_heavy_list, n_heavy, n_items, i_pad,
-                                                       (__nv_bfloat16 *)d_bt, d_wd, flags);
+                                                       (__nv_bfloat16 *)d_bt, d_wd, d_wd + (size_t)n_heavy * n_items, flags);
         RT_CHECK_LAUNCH();
     }
     if (w_nnz > 0) {
@@ -645,12 +704,12 @@ extern "C" int rt_values_bf16_exact(const float *d_vals, int64_t n, int32_t *h_n
 
 extern "C" int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval, const int32_t *d_users,
                                     int32_t n_query, const int32_t *d_wrptr, const int32_t *d_wridx, const float *d_wrval,
-                                    const int32_t *d_heavy_of, const void *d_bt, const float *d_wd, int32_t n_items, int32_t k,
+                                    const int32_t *d_heavy_of, int32_t n_heavy, const void *d_bt, const float *d_wd, int32_t n_items, int32_t k,
                                     int32_t filter_interacted, int32_t mode, int32_t x_planes, int32_t *d_tc_ids,
                                     float *d_tc_scores, int32_t *d_tc_cnt, int32_t *d_out_ids, float *d_out_scores,
                                     int32_t *d_out_cnt, int32_t *d_fallback, float *d_dbg_scores, void *stream) {
     RT_ARG(k >= 1 && k <= TC_KLIST, "k must be in [1,16] for the tensor-core path");
-    RT_ARG(n_items > 0 && (mode == RT_TOPK_DENSE || mode == RT_TOPK_SPARSE) && (x_planes == 1 || x_planes == 3), "arguments");
+    RT_ARG(n_items > 0 && (mode == RT_TOPK_DENSE || mode == RT_TOPK_SPARSE) && (x_planes == 1 || x_planes == 3) && n_heavy >= 1 && n_heavy <= TC_KH, "arguments");
     if (n_query <= 0) return RT_OK;
     RT_ARG(d_rptr && d_users && d_wrptr && d_heavy_of && d_bt && d_wd && d_tc_ids && d_tc_scores && d_tc_cnt && d_out_ids &&
                d_out_scores && d_out_cnt && d_fallback, "null pointer");
@@ -679,7 +738,7 @@ extern "C" int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx
     const int n_blocks = (n_query + TC_M - 1) / TC_M;
     int grid = rt::sm_count();
     if (grid > n_blocks) grid = n_blocks;
-    const size_t smem = 1024 + (size_t)(x_planes + TC_STAGES * 3) * TC_TILE_BYTES + (size_t)TC_KLIST * TC_M * 8 + 16 * 8 + 64;
+    const size_t smem = 1024 + (size_t)(x_planes + TC_STAGES * 3) * TC_TILE_BYTES + (size_t)2 * TC_KLIST * TC_M * 8 + 16 * 8 + 64;
     if (x_planes == 1) {
         RT_CUDA(cudaFuncSetAttribute(recommend_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         recommend_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(tmap, P);
@@ -698,8 +757,9 @@ extern "C" int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx
     int fgrid = rt::sm_count() * 3;
     if (fgrid > n_query) fgrid = n_query;
     recommend_tcfix_kernel<<<fgrid, FX_NT, fsmem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of,
-                                                      d_wd, n_items, k, filter_interacted, mode == RT_TOPK_DENSE ? 1 : 0, d_tc_ids,
-                                                      d_tc_scores, d_tc_cnt, d_out_ids, d_out_scores, d_out_cnt, d_fallback, d_next);
+                                                      d_wd, d_wd + (size_t)n_heavy * n_items, n_items, k, filter_interacted,
+                                                      mode == RT_TOPK_DENSE ? 1 : 0, d_tc_ids, d_tc_scores, d_out_ids, d_out_scores,
+                                                      d_out_cnt, d_fallback, d_next);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -51,6 +51,8 @@ struct SolveArgs {
     const int *only_flagged;  // when set, the block kernel solves only targets t with only_flagged[t] != 0
     int flag_mod;             // test hook (solve_impl = 3): the warp kernel hands every flag_mod-th target to the block kernel
     int skip_trivial;  // nn mode: targets without a live coordinate return no pairs (rt_fit_config.skip_trivial)
+    int hit_mode;      // all-features mode: shared-memory bitmap of the live positions of active[] + per-sweep hit lists
+    int bm_off;        // byte offset of the bitmap in dynamic shared memory (hit_mode)
     int hot_in_smem;  // per-visit arrays live in dynamic shared memory
     int use_gs;       // dense live x live Gram block cached in shared memory (nn mode)
 };
@@ -129,6 +131,13 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
     uint32_t *ckey = (uint32_t *)take(cold, co, sizeof(uint32_t) * NU);
     int *cidx = (int *)take(cold, co, sizeof(int) * NU);
     unsigned char *excl = (unsigned char *)take(cold, co, NU);
+    // hit mode (all features, few live coordinates): bit idx of bm = "active[idx] is a live coordinate"; a sweep then scans
+    // its n_active draws against the bitmap with every warp (no dependent global loads) and the sequential walker only
+    // sees the handful of draws that land on a live coordinate -- same visits in the same order as the plain walk
+    constexpr int HITCAP = 256;
+    uint32_t *bm = A.hit_mode ? (uint32_t *)(dyn_smem + A.bm_off) : nullptr;
+    int *whits = A.hit_mode ? (int *)(dyn_smem + A.bm_off + (((size_t)(NU + 31) / 32 * 4 + 15) & ~(size_t)15)) : nullptr;
+    bool bm_valid = false;
 
 
     for (;;) {
@@ -307,6 +316,17 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
                 __syncthreads();
             }
             n_active = na;
+            bm_valid = false;
+            if (A.hit_mode && (long long)m * 16 < na) {
+                for (int base = 0; base < na; base += NT) {   // NT = 128: base + 32 * warp is a multiple of 32
+                    const int idx = base + tid;
+                    const bool lv = idx < na && live_slot[active[idx]] >= 0;
+                    const unsigned word = __ballot_sync(0xffffffffu, lv);
+                    if (lane == 0) bm[(base >> 5) + warp] = word;
+                }
+                __syncthreads();
+                bm_valid = true;
+            }
         };
 
         eval_gap();
@@ -317,19 +337,56 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
             int64_t tdraw = 0;  // index of the next draw in the rng table
             for (int it = 0; it < A.max_iter; ++it) {
                 // ---------------- one sweep: n_active draws ----------------
+                int n_visit = n_active;
+                bool hits = false;
+                if (bm_valid) {
+                    // phase A: warp w scans draws [w * seg, (w + 1) * seg) and lists, in order, those that hit a live position
+                    const int seg = (n_active + nwarps - 1) / nwarps;
+                    const int d0 = warp * seg, d1 = min(d0 + seg, n_active);
+                    int cntw = 0;
+                    for (int db = d0; db < d1; db += 32) {
+                        const int d = db + lane;
+                        bool hit = false;
+                        int idx = 0;
+                        if (d < d1) {
+                            idx = (int)(A.rng[tdraw + d] % (uint32_t)n_active);
+                            hit = (bm[idx >> 5] >> (idx & 31)) & 1u;
+                        }
+                        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                        if (bal) {
+                            const int pos = cntw + __popc(bal & ((1u << lane) - 1u));
+                            if (hit && pos < HITCAP) whits[warp * HITCAP + pos] = idx;
+                            cntw += __popc(bal);
+                        }
+                    }
+                    if (lane == 0) ms.wtot[0][1][warp] = cntw;
+                    __syncthreads();
+                    int tot = 0;
+                    bool fits = true;
+                    for (int ww = 0; ww < nwarps; ++ww) { tot += ms.wtot[0][1][ww]; fits = fits && ms.wtot[0][1][ww] <= HITCAP; }
+                    if (fits) { hits = true; n_visit = tot; }   // (a warp list overflowed: plain walk for this sweep)
+                }
                 int v = 0;
                 double wmax_l = 0.0, dwmax_l = 0.0;  // per-lane running maxima (warp 0)
                 for (;;) {
                     if (warp == 0) {
                         int kind = 0;
-                        while (v < n_active) {
-                            const int nb = min(32, n_active - v);
+                        while (v < n_visit) {
+                            const int nb = min(32, n_visit - v);
                             bool upd = false;
                             int s = -1;
                             double wc = 0.0, wn = 0.0;
                             if (lane < nb) {
-                                const uint32_t r = A.rng[tdraw + lane];
-                                const int k = active[r % (uint32_t)n_active];
+                                int k;
+                                if (hits) {
+                                    // visit v + lane of the concatenated per-warp lists
+                                    int i = v + lane, ww = 0;
+                                    while (i >= ms.wtot[0][1][ww]) { i -= ms.wtot[0][1][ww]; ++ww; }
+                                    k = active[whits[ww * HITCAP + i]];
+                                } else {
+                                    const uint32_t r = A.rng[tdraw + v + lane];
+                                    k = active[r % (uint32_t)n_active];
+                                }
                                 s = live_slot[k];
                                 if (s >= 0) {
                                     wc = w[s];
@@ -347,7 +404,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
                             const unsigned mask = __ballot_sync(0xffffffffu, upd);
                             if (mask == 0u) {
                                 wmax_l = fmax(wmax_l, fabs(wn));
-                                v += nb; tdraw += nb;
+                                v += nb;
                                 continue;
                             }
                             const int L0 = __ffs(mask) - 1;
@@ -356,7 +413,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
                                 dwmax_l = fmax(dwmax_l, fabs(wn - wc));
                                 ms.ev_slot = s; ms.ev_delta = wn - wc; ms.ev_wnew = wn;
                             }
-                            v += L0 + 1; tdraw += L0 + 1;
+                            v += L0 + 1;
                             kind = 1;
                             break;
                         }
@@ -376,6 +433,7 @@ __global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
                     }
                     __syncthreads();
                 }
+                tdraw += n_active;
                 draws += n_active;
                 n_iter = it + 1;
                 const double w_max = ms.w_max, d_w_max = ms.d_w_max;
@@ -986,7 +1044,7 @@ extern "C" int rt_rng_table(uint32_t seed, int64_t n, uint32_t *d_out, void *str
 
 namespace {
 struct SolvePlan {
-    int NU, NT, grid, hot_in_smem, use_gs;
+    int NU, NT, grid, hot_in_smem, use_gs, hit_mode, bm_off;
     size_t hot_bytes, cold_bytes, smem_bytes, scratch_per_cta;
 };
 
@@ -1005,12 +1063,20 @@ SolvePlan make_plan(int n_items, int nn, int n_targets) {
     p.hot_bytes = hot;
     p.cold_bytes = cold;
     p.smem_bytes = p.hot_in_smem ? hot : 0;
+    // all-features mode: live-position bitmap + per-warp hit lists (4 warps x 256 draws) behind the hot arrays
+    p.hit_mode = 0; p.bm_off = 0;
+    if (nn == 0) {
+        const size_t bm_bytes = pad((NU + 31) / 32 * 4) + 4 * 256 * sizeof(int);
+        if (p.smem_bytes + bm_bytes + static_smem <= (size_t)optin - 1024) {
+            p.hit_mode = 1; p.bm_off = (int)p.smem_bytes; p.smem_bytes += bm_bytes;
+        }
+    }
     p.scratch_per_cta = rt::align_up(cold + (p.hot_in_smem ? 0 : hot) + 256, 256);
     p.NT = 128;  // multiple of 128: the fast candidate selection uses 128 strided buckets
     // resident CTAs per SM, bounded by shared memory
     int per_sm = nn > 0 ? 8 : 4;
     if (p.hot_in_smem) {
-        int fit = (int)(((size_t)optin) / (hot + static_smem + 1024));
+        int fit = (int)(((size_t)optin) / (p.smem_bytes + static_smem + 1024));
         if (fit < 1) fit = 1;
         if (fit < per_sm) per_sm = fit;
     }
@@ -1060,6 +1126,7 @@ static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t
     A.scratch = (char *)d_workspace + 1024 + diag_bytes;
     A.scratch_per_cta = p.scratch_per_cta;
     A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
+    A.hit_mode = rt::option(rt::OPT_SOLVE_IMPL) == 1 ? 0 : p.hit_mode; A.bm_off = p.bm_off;
     A.only_flagged = nullptr;
     A.skip_trivial = (cfg->nn > 0 && cfg->skip_trivial && cfg->positive && cfg->nonneg && !d_sel_out && !d_sel_in) ? 1 : 0;
     A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;

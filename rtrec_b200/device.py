@@ -471,7 +471,7 @@ class TcPack:
 
 TC_MIN_QUERIES = 4096   # below this the exact kernel is used (a launch of the tensor-core pipeline does not pay)
 TC_KMAX = 16
-_score_tc = 1           # 0 = never use the tensor-core scoring path
+_score_tc = 1           # 0 = never use the tensor-core scoring path (set_option("score_tc", 0))
 
 
 def tc_pack(W: DeviceW) -> Optional[TcPack]:
@@ -525,12 +525,12 @@ def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: 
     if not x_nonneg:
         return None
     ids = empty(Q * k, t.int32); scores = empty(Q * k, t.float32); cnt = empty(Q, t.int32)
-    tc_ids = empty(Q * 16, t.int32); tc_sc = empty(Q * 16, t.float32); tc_cnt = empty(Q, t.int32)
+    tc_ids = empty(Q * 32, t.int32); tc_sc = empty(Q * 32, t.float32); tc_cnt = empty(Q, t.int32)
     fb = empty(Q, t.int32)
     i_pad = (W.n_items + 127) // 128 * 128
     dbg = t.zeros((Q, i_pad), dtype=t.float32, device=dev()) if debug_scores else None
     check(_lib.load().rt_slim_recommend_tc(ptr(X.rptr), ptr(X.ridx), ptr(X.rval), ptr(users), Q, ptr(W.wrptr), ptr(W.wridx),
-                                           ptr(W.wrval), ptr(pk.heavy_of), ptr(pk.bt), ptr(pk.wd), W.n_items, int(k),
+                                           ptr(W.wrval), ptr(pk.heavy_of), pk.n_heavy, ptr(pk.bt), ptr(pk.wd), W.n_items, int(k),
                                            1 if filter_interacted else 0, int(mode), 1 if x_exact else 3, ptr(tc_ids), ptr(tc_sc),
                                            ptr(tc_cnt), ptr(ids), ptr(scores), ptr(cnt), ptr(fb), ptr(dbg), stream_ptr()),
           "rt_slim_recommend_tc")
@@ -545,7 +545,7 @@ def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: 
             _score_tc = keep
         ids[redo] = r_ids; scores[redo] = r_sc; cnt[redo] = r_cnt
     if debug_scores:
-        return ids, scores, cnt, dbg, (tc_ids.view(Q, 16), tc_sc.view(Q, 16), tc_cnt), redo
+        return ids, scores, cnt, dbg, (tc_ids.view(Q, 32), tc_sc.view(Q, 32), tc_cnt), redo
     return ids, scores, cnt
 
 

@@ -141,3 +141,46 @@ def _sel_for(m, items):
         return sel
     pos = {int(j): k for k, j in enumerate(order.tolist())}
     return sel[[pos[int(j)] for j in items]]
+
+
+def test_hybrid_call_pattern_ret_scores():
+    """the way HybridSlimFM drives the operator (/root/reference/rtrec/models/hybrid.py:215-269,
+    369-432): ``slim_model.fit(csc, parallel=True)``, then ``recommend`` / ``recommend_batch`` on a CSR that only holds
+    the rows of the queried users (``to_csr(select_users=...)``), with and without candidates, ``ret_scores=True``; ids
+    and float32 scores against the oracle (ties aside), for both id kinds (dense_output follows ``pass_through``)."""
+    from rtrec_b200.models import SLIM
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    u, i, ts, r = synth_events(700, 260, 18000, seed=41, rating="cont")
+    m = SLIM()                                        # store only: the operator below is driven by hand, like hybrid.py
+    m.add_interaction_arrays(u, i, ts, r)
+    op = SLIMElastic({"nn_feature_selection": 30})
+    ui_csc = m.interactions.to_csc()
+    op.fit(ui_csc, parallel=True)                     # hybrid.py:217
+    o = so.SlimOracle({"nn_feature_selection": 30})
+    o.item_similarity = op.item_similarity           # same W: this test is about the scoring calls
+    users = [3, 17, 99, 250, 613]
+    ui_csr = m.interactions.to_csr(select_users=users)     # rows of other users are empty (hybrid.py:389)
+    full = m.interactions.to_csr()
+    assert ui_csr.shape == full.shape and ui_csr.nnz == sum(full[x].nnz for x in users)
+    cand = list(range(5, 200, 3))
+    for dense_output in (True, False):
+        for candidates in (None, cand):
+            got = op.recommend_batch(users, ui_csr, candidate_item_ids=candidates, top_k=8, filter_interacted=True,
+                                     dense_output=dense_output, ret_scores=True)             # hybrid.py:402
+            exp = o.recommend_batch(users, ui_csr, candidate_item_ids=candidates, top_k=8, filter_interacted=True,
+                                    dense_output=dense_output, ret_scores=True)
+            for (gi, gs), (ei, es) in zip(got, exp):
+                assert isinstance(gi, list) and isinstance(gs, np.ndarray) and gs.dtype == np.float32
+                assert len(gi) == len(ei)
+                np.testing.assert_allclose(gs, es, rtol=2e-5, atol=1e-7)
+                if len(set(np.round(es, 6))) == len(es):                                          # untied: identical ids
+                    assert gi == ei
+        one_ids, one_sc = op.recommend(users[1], m.interactions.to_csr(select_users=[users[1]]), top_k=8,
+                                       filter_interacted=True, dense_output=dense_output, ret_scores=True)   # hybrid.py:264
+        ref_ids, ref_sc = o.recommend_batch([users[1]], full, top_k=8, filter_interacted=True, dense_output=dense_output,
+                                            ret_scores=True)[0]
+        np.testing.assert_allclose(one_sc, ref_sc, rtol=2e-5, atol=1e-7)
+        assert len(one_ids) == len(ref_ids)
+    ids, sc = op.similar_items(7, top_k=5, ret_ndarrays=True)                                       # hybrid.py similar path
+    ref = o.similar_items(7, top_k=5)
+    assert ids.tolist() == [a for a, _ in ref] and np.allclose(sc, [b for _, b in ref])
