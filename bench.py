@@ -470,6 +470,12 @@ def fit_phases(c, args, X, op, mark):
     cfg = op._config(X)
     rank, world = c.rank, c.world
     res = None
+    if int(cfg.nn) == 0:
+        # all features: only the Gram rows that can carry a non-zero solution (every rank does this small fit itself)
+        res = D.fit_pruned(X, t.arange(X.n_items, dtype=t.int32, device="cuda"), cfg)
+        if res is not None:
+            mark("fit_pruned")
+            return res
     if world > 1 and args.exchange == "rows" and args.scoring == "query":
         # owner-rows fit: no full Gram exchange (None = CUDA IPC unavailable on this node, agreed by all ranks)
         res = P.fit_owner_rows(X, cfg, rank=rank, world=world, marks=mark)
@@ -520,7 +526,7 @@ def kernel_bytes(c, X, W, res, world):
 def roofline_of(c, args, phase_ms, gram_bytes, solve_bytes, rec_bytes, rec_key="recommend"):
     peak, peak_src = load_peaks()
     gram_ms = sum(phase_ms.get(k, 0.0) for k in ("gram_lower", "gram_finish", "gram_finish_p2p", "gram_rows", "gram_exchange"))
-    kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0), solve_bytes),
+    kern = {"gram": (gram_ms, gram_bytes), "solve": (phase_ms.get("solve", 0.0) + phase_ms.get("fit_pruned", 0.0), solve_bytes),
             "recommend": (phase_ms.get(rec_key, 0.0), rec_bytes)}
     dom = max(kern, key=lambda k: kern[k][0])
     ach = kern[dom][1] / (kern[dom][0] / 1e3) / 1e9 if kern[dom][0] > 0 else 0.0

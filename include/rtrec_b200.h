@@ -307,6 +307,24 @@ int rt_slim_solve_rows(const void *const *h_bases, int32_t n_bases, const int32_
                        int64_t out_cap, int64_t *h_needed, int32_t *d_stats, void *stream);
 
 /*
+ * All-features fit (nn == 0) with positive coefficients on non-negative data WITHOUT the dense Gram matrix (same result
+ * contract as rt_gram_lower + rt_gram_finish + rt_slim_solve; replaces slim_elastic.py:229-281 for that configuration).
+ * A coordinate c of target j can only leave 0 if G[j][c] > alpha*l1_ratio*n_samples, and G[j][c] <= sqrt(G[j][j] G[c][c]):
+ * one pass over X (column sums of squares) names the items that can take part in any non-zero solution; only their Gram
+ * rows are formed (library scratch, n_rows x n_items floats) and only they are solved, every other target is returned
+ * as the zero column.  *h_n_rows = number of candidate items; *h_used = 1 if the fit was done this way, 0 if the path
+ * does not apply (cfg) or the candidates exceed a quarter of the catalogue -- outputs are then untouched and the caller
+ * takes the dense path.  Matrix arguments as rt_gram_lower (+ d_ccol, the COO column id of every CSC entry), solver
+ * arguments and outputs as rt_slim_solve.  Synchronises.
+ */
+int rt_slim_fit_pruned(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                       const float *d_cval, const int32_t *d_ccol, const int32_t *d_rptr, const int32_t *d_ridx,
+                       const float *d_rval, int64_t nnz, const int32_t *d_targets, int32_t n_targets,
+                       const rt_fit_config *cfg, const uint32_t *d_rng, int64_t rng_len, int64_t *d_out_off,
+                       int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                       int64_t *h_needed, int32_t *d_stats, int32_t *h_used, int32_t *h_n_rows, void *stream);
+
+/*
  * Assemble / merge the item-similarity matrix W (CSC, n_items x n_items) from solver output,
  * with the LIL-assignment semantics of slim_elastic.py:273-274, 371-374, 556-557:
  * for every returned pair (i, v) of target j: v != 0 sets W[i,j] = v, v == 0 deletes W[i,j];

@@ -81,6 +81,8 @@ PROTOTYPES = {
                                      _I64, C.POINTER(_I64), _P, _P]),
     "rt_slim_solve": (C.c_int, [_P, _I64, _I32, _P, _I32, C.POINTER(FitConfig), _P, _P, _I64, _P, _P, _P, _P, _P, _I64,
                                 C.POINTER(_I64), _P, _P]),
+    "rt_slim_fit_pruned": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _I32, C.POINTER(FitConfig), _P, _I64, _P, _P,
+                                     _P, _P, _I64, C.POINTER(_I64), _P, C.POINTER(_I32), C.POINTER(_I32), _P]),
     "rt_w_merge": (C.c_int, [_I32, _P, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _I64, C.POINTER(_I64), _P]),
     "rt_transpose": (C.c_int, [_I32, _I32, _P, _P, _P, _I64, _P, _P, _P, _P]),
     "rt_slim_recommend": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),

@@ -18,7 +18,7 @@ int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).
 void *scratch(int slot, size_t bytes);
-enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_GRAM_PACK, SCR_SLOTS };
+enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_GRAM_PACK, SCR_GRAM_SEL, SCR_SLOTS };
 
 #define RT_CUDA(expr)                                                                              \
     do {                                                                                           \
@@ -71,6 +71,9 @@ int rt_launch_recommend2(const int32_t *d_rptr, const int32_t *d_ridx, const flo
                          int32_t n_items, int32_t j_begin, int32_t j_end, int32_t k, int32_t filter_interacted,
                          int32_t mode, int32_t *d_out_ids, float *d_out_scores, int32_t *d_out_cnt, int *d_next,
                          cudaStream_t st);
+int rt_gram_rows_selected(const int32_t *d_ccol, const int32_t *d_cidx, const float *d_cval, int64_t nnz, const int32_t *d_rptr,
+                          const int32_t *d_ridx, const float *d_rval, const int32_t *d_row_slot, float *d_G, int64_t ldg,
+                          cudaStream_t st);
 extern "C" int rt_csr_split(int32_t n_rows, const int32_t *d_ptr, const int32_t *d_idx, int32_t base,
                             int32_t range_width, int32_t n_ranges, int32_t *d_seg, void *stream);
 namespace rt {

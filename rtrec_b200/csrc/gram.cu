@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(GRAM_WARPS * 32)
 gram_rows_kernel(const int *__restrict__ ccol, const int *__restrict__ cidx, const float *__restrict__ cval,
                  int64_t e_begin, int64_t e_end, const int *__restrict__ rptr, const int *__restrict__ ridx,
                  const float *__restrict__ rval, float *__restrict__ G, int64_t ldg,
-                 unsigned long long *__restrict__ counter) {
+                 unsigned long long *__restrict__ counter, const int *__restrict__ row_slot) {
+    // row_slot (optional): only the Gram rows of the items with row_slot[j] >= 0 are formed, row j at G + row_slot[j] * ldg
     const int lane = threadIdx.x & 31;
     for (;;) {
         unsigned long long c = 0;
@@ -35,11 +36,15 @@ gram_rows_kernel(const int *__restrict__ ccol, const int *__restrict__ cidx, con
         float y = 0.f;
         if (e < e_end) {
             j = ccol[e];
-            const int u = cidx[e];
-            y = cval[e];
-            r0 = rptr[u];
-            r1 = rptr[u + 1];
+            if (row_slot) j = row_slot[j];
+            if (j >= 0) {
+                const int u = cidx[e];
+                y = cval[e];
+                r0 = rptr[u];
+                r1 = rptr[u + 1];
+            }
         }
+        if (row_slot && !__any_sync(0xffffffffu, r1 > r0)) continue;   // none of these 32 entries belongs to a wanted row
         const int nb = (int)min((int64_t)32, e_end - base);
         for (int l = 0; l < nb; ++l) {
             const int jj = __shfl_sync(0xffffffffu, j, l);
@@ -80,7 +85,24 @@ extern "C" int rt_gram_rows(const int32_t *d_ccol, const int32_t *d_cidx, const 
     const int64_t cap = (int64_t)rt::sm_count() * 8;       // persistent: 8 CTAs x 8 warps per SM
     if (grid > cap) grid = cap;
     gram_rows_kernel<<<(unsigned)grid, GRAM_WARPS * 32, 0, st>>>(d_ccol, d_cidx, d_cval, e_begin, e_end, d_rptr, d_ridx,
-                                                                d_rval, d_G, ldg, d_counter);
+                                                                d_rval, d_G, ldg, d_counter, nullptr);
+    RT_CHECK_LAUNCH();
+    return RT_OK;
+}
+
+// Gram rows of selected items only (internal; used by rt_slim_fit_pruned): d_row_slot[j] = row of item j in d_G or -1
+int rt_gram_rows_selected(const int32_t *d_ccol, const int32_t *d_cidx, const float *d_cval, int64_t nnz, const int32_t *d_rptr,
+                          const int32_t *d_ridx, const float *d_rval, const int32_t *d_row_slot, float *d_G, int64_t ldg,
+                          cudaStream_t st) {
+    if (nnz <= 0) return RT_OK;
+    static unsigned long long *d_counter = nullptr;
+    if (!d_counter) RT_CUDA(cudaMalloc(&d_counter, sizeof(unsigned long long)));
+    RT_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), st));
+    int64_t grid = ((nnz + 31) / 32 + GRAM_WARPS - 1) / GRAM_WARPS;
+    const int64_t cap = (int64_t)rt::sm_count() * 8;
+    if (grid > cap) grid = cap;
+    gram_rows_kernel<<<(unsigned)grid, GRAM_WARPS * 32, 0, st>>>(d_ccol, d_cidx, d_cval, 0, nnz, d_rptr, d_ridx, d_rval, d_G, ldg,
+                                                                d_counter, d_row_slot);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -415,6 +415,58 @@ recommend_sparse_kernel(const int *__restrict__ rptr, const int *__restrict__ ri
         const int q = order[qi];
         const int u = users[q];
         const int r0 = rptr[u], r1 = rptr[u + 1];
+        // ---- at most 32 entries behind a row of at most 32 items: everything in registers (no table to clear and scan)
+        if (r1 - r0 <= 32) {
+            const int p = r0 + lane;
+            int a = 0, b = 0, item = -1;
+            float x = 0.f;
+            if (p < r1) {
+                item = ridx[p];
+                x = rval[p];
+                a = wrptr[item]; b = wrptr[item + 1];
+                if (!whole && b > a) { a = lower_bound3(wridx, a, b, j_begin); b = lower_bound3(wridx, a, b, j_end); }
+            }
+            int incl = b - a;                                   // inclusive prefix of the entry counts
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t_; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total <= 32) {
+                // entry e (ascending item, then ascending column) -> lane e, staged through the (unused) table memory
+                for (int e = 0; e < b - a; ++e) { key[incl - (b - a) + e] = wridx[a + e]; val[incl - (b - a) + e] = __fmul_rn(x, wrval[a + e]); }
+                __syncwarp();
+                const int j = lane < total ? key[lane] : -1 - lane;      // distinct negative ids for the unused lanes
+                const float v = lane < total ? val[lane] : 0.0f;
+                // score of column j = its entries added in ascending source-item order, starting from 0 (scipy's order);
+                // the first lane holding j keeps it
+                float acc = 0.0f;
+                bool first = true, interacted = false;
+#pragma unroll 4
+                for (int l = 0; l < 32; ++l) {
+                    const int jl = __shfl_sync(0xffffffffu, j, l);
+                    const float vl = __shfl_sync(0xffffffffu, v, l);
+                    const int il = __shfl_sync(0xffffffffu, item, l);
+                    if (jl == j) { acc = __fadd_rn(acc, vl); if (l < lane) first = false; }
+                    if (filter && il == j) interacted = true;
+                }
+                __syncwarp();
+                const bool cand = lane < total && first && !interacted && acc != 0.0f;
+                const uint32_t fk = cand ? float_key(acc) : 0u;
+                int rank = 0;
+#pragma unroll 4
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t kl = __shfl_sync(0xffffffffu, fk, l);
+                    const int jl = __shfl_sync(0xffffffffu, j, l);
+                    const bool cl = __shfl_sync(0xffffffffu, (int)cand, l) != 0;
+                    rank += cl && (kl > fk || (kl == fk && jl > j));
+                }
+                if (cand && rank < k) { out_ids[(size_t)q * k + rank] = j; out_scores[(size_t)q * k + rank] = acc; }
+                const int cnt = min(k, __popc(__ballot_sync(0xffffffffu, cand)));
+                for (int e = cnt + lane; e < k; e += 32) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+                if (lane == 0) out_cnt[q] = cnt;
+                __syncwarp();
+                continue;
+            }
+        }
         for (int s = lane; s < SP_SLOTS; s += 32) key[s] = -1;
         __syncwarp();
         // ---- accumulate, row by row in ascending item order

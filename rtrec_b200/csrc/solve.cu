@@ -51,6 +51,7 @@ struct SolveArgs {
     const int *only_flagged;  // when set, the block kernel solves only targets t with only_flagged[t] != 0
     int flag_mod;             // test hook (solve_impl = 3): the warp kernel hands every flag_mod-th target to the block kernel
     int skip_trivial;  // nn mode: targets without a live coordinate return no pairs (rt_fit_config.skip_trivial)
+    const int *item_flag;  // pruned fit: items whose Gram row exists (others are trivial targets and are never dereferenced)
     int hit_mode;      // all-features mode: shared-memory bitmap of the live positions of active[] + per-sweep hit lists
     int bm_off;        // byte offset of the bitmap in dynamic shared memory (hit_mode)
     int hot_in_smem;  // per-visit arrays live in dynamic shared memory
@@ -99,7 +100,10 @@ __device__ __forceinline__ void block_sum4(double &v0, double &v1, double &v2, d
     for (int w = 1; w < nw; ++w) { v0 += ms->red[0][w]; v1 += ms->red[1][w]; v2 += ms->red[2][w]; v3 += ms->red[3][w]; }
 }
 
-__global__ void __launch_bounds__(128, 8) slim_solve_kernel(SolveArgs A) {
+// MAXT = 128 (feature selection: eight CTAs per SM, the candidate selection wants 128 threads) or 512 (all features: the
+// universe loops over tens of thousands of coordinates are what a column costs)
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 128 ? 8 : 2) slim_solve_kernel(SolveArgs A) {
     extern __shared__ __align__(16) char dyn_smem[];
     __shared__ Misc ms;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -942,11 +946,13 @@ __global__ void __launch_bounds__(256) live_prefilter_kernel(SolveArgs A, int *_
     const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (t >= A.n_targets) return;
     const int j = A.targets[t];
-    const float *gj = g_row(A, j);
     const int N = A.n_items;
     const double a = A.a;
+    const bool have_row = !A.item_flag || A.item_flag[j] != 0;
+    const float *gj = have_row ? g_row(A, j) : nullptr;
     const bool vec4 = ((A.ldg & 3) == 0) && ((((uintptr_t)gj) & 15) == 0);
     bool any = false;
+    if (have_row) {
     const int N4 = vec4 ? (N >> 2) : 0;
     for (int q = lane; q < N4 && !any; q += 32 * 4) {
         float4 v[4];
@@ -960,6 +966,7 @@ __global__ void __launch_bounds__(256) live_prefilter_kernel(SolveArgs A, int *_
         }
     }
     for (int i = (N4 << 2) + lane; i < N; i += 32) any = any || (i != j && (double)gj[i] > a);
+    }
     any = __any_sync(0xffffffffu, any);
     if (lane == 0) {
         flags[t] = any ? 1 : 0;
@@ -1063,18 +1070,18 @@ SolvePlan make_plan(int n_items, int nn, int n_targets) {
     p.hot_bytes = hot;
     p.cold_bytes = cold;
     p.smem_bytes = p.hot_in_smem ? hot : 0;
-    // all-features mode: live-position bitmap + per-warp hit lists (4 warps x 256 draws) behind the hot arrays
+    // all-features mode: live-position bitmap + per-warp hit lists (16 warps x 256 draws) behind the hot arrays
     p.hit_mode = 0; p.bm_off = 0;
     if (nn == 0) {
-        const size_t bm_bytes = pad((NU + 31) / 32 * 4) + 4 * 256 * sizeof(int);
+        const size_t bm_bytes = pad((NU + 31) / 32 * 4) + 16 * 256 * sizeof(int);
         if (p.smem_bytes + bm_bytes + static_smem <= (size_t)optin - 1024) {
             p.hit_mode = 1; p.bm_off = (int)p.smem_bytes; p.smem_bytes += bm_bytes;
         }
     }
     p.scratch_per_cta = rt::align_up(cold + (p.hot_in_smem ? 0 : hot) + 256, 256);
-    p.NT = 128;  // multiple of 128: the fast candidate selection uses 128 strided buckets
+    p.NT = nn > 0 ? 128 : 512;  // multiple of 128: the fast candidate selection uses 128 strided buckets
     // resident CTAs per SM, bounded by shared memory
-    int per_sm = nn > 0 ? 8 : 4;
+    int per_sm = nn > 0 ? 8 : 2;
     if (p.hot_in_smem) {
         int fit = (int)(((size_t)optin) / (p.smem_bytes + static_smem + 1024));
         if (fit < 1) fit = 1;
@@ -1089,6 +1096,7 @@ SolvePlan make_plan(int n_items, int nn, int n_targets) {
 }  // namespace
 
 static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t n_bases, const int32_t *d_rowslot,
+                           const float *d_diag_in, const int32_t *d_item_flag,
                            int64_t ldg, int32_t n_items, const int32_t *d_targets,
                            int32_t n_targets, const rt_fit_config *cfg, const int32_t *d_sel_in,
                            const uint32_t *d_rng, int64_t rng_len, int32_t *d_sel_out, int64_t *d_out_off,
@@ -1128,13 +1136,17 @@ static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t
     A.hot_in_smem = p.hot_in_smem; A.use_gs = p.use_gs;
     A.hit_mode = rt::option(rt::OPT_SOLVE_IMPL) == 1 ? 0 : p.hit_mode; A.bm_off = p.bm_off;
     A.only_flagged = nullptr;
+    A.item_flag = d_item_flag;
     A.skip_trivial = (cfg->nn > 0 && cfg->skip_trivial && cfg->positive && cfg->nonneg && !d_sel_out && !d_sel_in) ? 1 : 0;
     A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;
     RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
     A.diag = nullptr;
-    gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(A, n_items, d_diag);
-    A.diag = d_diag;
-    RT_CHECK_LAUNCH();
+    if (d_diag_in) A.diag = d_diag_in;     // pruned fit: the diagonal comes from X (most Gram rows do not exist)
+    else {
+        gather_diag_kernel<<<(n_items + 255) / 256, 256, 0, st>>>(A, n_items, d_diag);
+        A.diag = d_diag;
+        RT_CHECK_LAUNCH();
+    }
     bool block_pass = true;
     if (cfg->nn > 0 && p.NU <= SW_MAXU && rt::option(rt::OPT_SOLVE_IMPL) != 1) {
         // warp-per-column kernel; columns it cannot take (candidate-list overflow) are flagged for the block kernel
@@ -1176,8 +1188,13 @@ static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t
         A.only_flagged = d_flags;
     }
     if (block_pass) {
-        RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        slim_solve_kernel<<<p.grid, p.NT, p.smem_bytes, st>>>(A);
+        if (p.NT == 128) {
+            RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+            slim_solve_kernel<128><<<p.grid, p.NT, p.smem_bytes, st>>>(A);
+        } else {
+            RT_CUDA(cudaFuncSetAttribute(slim_solve_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+            slim_solve_kernel<512><<<p.grid, p.NT, p.smem_bytes, st>>>(A);
+        }
         RT_CHECK_LAUNCH();
     }
     unsigned long long cur[2] = {0, 0};
@@ -1198,7 +1215,7 @@ extern "C" int rt_slim_solve(const float *d_G, int64_t ldg, int32_t n_items, con
                              int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
                              int64_t *h_needed, int32_t *d_stats, void *stream) {
     RT_ARG(d_G != nullptr || n_targets == 0, "null pointer");
-    return slim_solve_impl(d_G, nullptr, 0, nullptr, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len, d_sel_out,
+    return slim_solve_impl(d_G, nullptr, 0, nullptr, nullptr, nullptr, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len, d_sel_out,
                            d_out_off, d_out_cnt, d_out_rows, d_out_vals, out_cap, h_needed, d_stats, stream);
 }
 
@@ -1209,6 +1226,151 @@ extern "C" int rt_slim_solve_rows(const void *const *h_bases, int32_t n_bases, c
                                   int64_t out_cap, int64_t *h_needed, int32_t *d_stats, void *stream) {
     RT_ARG(h_bases && n_bases >= 1 && n_bases <= RT_MAX_PEERS && d_rowslot && (ldg % 4) == 0, "row buffers");
     for (int q = 0; q < n_bases; ++q) RT_ARG(h_bases[q] != nullptr && (((uintptr_t)h_bases[q]) & 15) == 0, "row buffer pointers");
-    return slim_solve_impl(nullptr, h_bases, n_bases, d_rowslot, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len,
+    return slim_solve_impl(nullptr, h_bases, n_bases, d_rowslot, nullptr, nullptr, ldg, n_items, d_targets, n_targets, cfg, d_sel_in, d_rng, rng_len,
                            d_sel_out, d_out_off, d_out_cnt, d_out_rows, d_out_vals, out_cap, h_needed, d_stats, stream);
+}
+
+// ================================================================================================
+// Pruned all-features fit: never forms the dense Gram matrix.
+//
+// With positive coefficients on non-negative data a coordinate c of target j can only leave 0 if G[j][c] > a
+// (a = alpha*l1_ratio*n_samples), and by Cauchy-Schwarz G[j][c] <= sqrt(G[j][j] G[c][c]).  So a target can have a non-zero
+// solution only if d_j * max_{c != j} d_c > a^2 with d = diag(G) = column sums of squares of X -- one pass over X.  At
+// the H&M shape (1.37M users: a = 13,720) that leaves 300 of 105,542 items; every other column is written as the zero
+// column at once, and only the Gram rows of the 300 candidates are formed (gram_rows_kernel with a row map) -- 127 MB
+// instead of 2 x 44.6 GB, and the solver's prefilter scans 300 rows instead of 105,542.  The candidate set is closed under
+// "is a live coordinate of", so the solver never dereferences a missing row; the diagonal for the screening rule comes
+// from d.  When the candidates are more than a quarter of the catalogue (small a: ML-1M shape) *h_used = 0 is returned
+// and the caller takes the dense path.
+namespace rt {
+
+__global__ void col_sumsq_kernel(const int *__restrict__ cptr, const float *__restrict__ cval, int n_items, float *__restrict__ d) {
+    const int lane = threadIdx.x & 31;
+    const int j = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (j >= n_items) return;
+    float s = 0.0f;
+    for (int e = cptr[j] + lane; e < cptr[j + 1]; e += 32) { const float v = cval[e]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) d[j] = s;
+}
+
+// two largest diagonal entries (one block)
+__global__ void __launch_bounds__(1024) top2_kernel(const float *__restrict__ d, int n, float *__restrict__ out) {
+    __shared__ float s1[32], s2[32];
+    float m1 = 0.f, m2 = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = d[i];
+        if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) m2 = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float a1 = __shfl_xor_sync(0xffffffffu, m1, o), a2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const float n1 = fmaxf(m1, a1);
+        m2 = fmaxf(fminf(m1, a1), fmaxf(m2, a2));
+        m1 = n1;
+    }
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = m1; s2[threadIdx.x >> 5] = m2; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m1 = threadIdx.x < (blockDim.x >> 5) ? s1[threadIdx.x] : 0.f;
+        m2 = threadIdx.x < (blockDim.x >> 5) ? s2[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float a1 = __shfl_xor_sync(0xffffffffu, m1, o), a2 = __shfl_xor_sync(0xffffffffu, m2, o);
+            const float n1 = fmaxf(m1, a1);
+            m2 = fmaxf(fminf(m1, a1), fmaxf(m2, a2));
+            m1 = n1;
+        }
+        if (threadIdx.x == 0) { out[0] = m1; out[1] = m2; }
+    }
+}
+
+// flag[j] = 1 iff item j can have a live coordinate (Cauchy-Schwarz with a 1e-3 safety margin on the fp32 sums)
+__global__ void cs_flag_kernel(const float *__restrict__ d, int n, const float *__restrict__ top2, double a2, int *__restrict__ flag) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float dj = d[j];
+    const float other = dj == top2[0] ? top2[1] : top2[0];
+    flag[j] = (dj > 0.0f && (double)dj * (double)other >= a2 * (1.0 - 1e-3)) ? 1 : 0;
+}
+
+// the solver takes y.y and the coordinate norms from the same numbers: diagonal of the rows that exist
+__global__ void diag_from_rows_kernel(const int *__restrict__ slot, int n, const float *__restrict__ rows, int64_t ld, float *__restrict__ d) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && slot[j] >= 0) d[j] = rows[(size_t)slot[j] * ld + j];
+}
+
+__global__ void slot_from_scan_kernel(const int *__restrict__ flag, const int *__restrict__ pos, int n, int *__restrict__ slot) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) slot[j] = flag[j] ? pos[j] : -1;      // single base buffer: (0 << 24) | row
+}
+
+}  // namespace rt
+
+#include <cub/cub.cuh>
+
+extern "C" int rt_slim_fit_pruned(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const int32_t *d_cidx,
+                                  const float *d_cval, const int32_t *d_ccol, const int32_t *d_rptr, const int32_t *d_ridx,
+                                  const float *d_rval, int64_t nnz, const int32_t *d_targets, int32_t n_targets,
+                                  const rt_fit_config *cfg, const uint32_t *d_rng, int64_t rng_len, int64_t *d_out_off,
+                                  int32_t *d_out_cnt, int32_t *d_out_rows, float *d_out_vals, int64_t out_cap,
+                                  int64_t *h_needed, int32_t *d_stats, int32_t *h_used, int32_t *h_n_rows, void *stream) {
+    RT_ARG(cfg && h_used && h_n_rows, "cfg / outputs");
+    *h_used = 0; *h_n_rows = 0;
+    if (h_needed) *h_needed = 0;
+    if (!(cfg->nn == 0 && cfg->positive && cfg->nonneg) || nnz <= 0 || n_targets <= 0) return RT_OK;   // not applicable
+    RT_ARG(n_users > 0 && n_items > 0 && n_items < (1 << 24) && d_cptr && d_cidx && d_cval && d_ccol && d_rptr && d_ridx && d_rval &&
+               d_targets, "matrix arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int I = n_items;
+    const int64_t ld = ((int64_t)I + 3) / 4 * 4;
+    // workspace: diag, top2, flag, pos, slot
+    const size_t wbytes = rt::align_up(sizeof(float) * (size_t)I) + 256 + 3 * rt::align_up(sizeof(int) * ((size_t)I + 1));
+    char *ws = (char *)rt::scratch(SCR_GRAM_PACK, wbytes);
+    if (!ws) return RT_ERR_CUDA;
+    float *d_diag = (float *)ws;
+    float *d_top2 = (float *)(ws + rt::align_up(sizeof(float) * (size_t)I));
+    int *d_flag = (int *)((char *)d_top2 + 256);
+    int *d_pos = (int *)((char *)d_flag + rt::align_up(sizeof(int) * ((size_t)I + 1)));
+    int *d_slot = (int *)((char *)d_pos + rt::align_up(sizeof(int) * ((size_t)I + 1)));
+    rt::col_sumsq_kernel<<<(unsigned)(((int64_t)I * 32 + 255) / 256), 256, 0, st>>>(d_cptr, d_cval, I, d_diag);
+    RT_CHECK_LAUNCH();
+    rt::top2_kernel<<<1, 1024, 0, st>>>(d_diag, I, d_top2);
+    RT_CHECK_LAUNCH();
+    const double a = (double)(float)(cfg->alpha * cfg->l1_ratio * (double)cfg->n_samples);
+    rt::cs_flag_kernel<<<(I + 255) / 256, 256, 0, st>>>(d_diag, I, d_top2, a * a, d_flag);
+    RT_CHECK_LAUNCH();
+    {
+        size_t tmp_bytes = 0;
+        RT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_flag, d_pos, I, st));
+        void *tmp = rt::scratch(SCR_CUB, tmp_bytes);
+        if (!tmp) return RT_ERR_CUDA;
+        RT_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_flag, d_pos, I, st));
+        rt::count_launch(1);
+    }
+    int last[2] = {0, 0};
+    RT_CUDA(cudaMemcpyAsync(&last[0], d_flag + I - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaMemcpyAsync(&last[1], d_pos + I - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RT_CUDA(cudaStreamSynchronize(st));
+    const int n_sel = last[0] + last[1];
+    *h_n_rows = n_sel;
+    if ((int64_t)n_sel * 4 > (int64_t)I) return RT_OK;    // too many candidate rows: the dense path is the better one
+    rt::slot_from_scan_kernel<<<(I + 255) / 256, 256, 0, st>>>(d_flag, d_pos, I, d_slot);
+    RT_CHECK_LAUNCH();
+    const size_t gbytes = sizeof(float) * (size_t)(n_sel > 0 ? n_sel : 1) * (size_t)ld;
+    float *d_rows = (float *)rt::scratch(SCR_GRAM_SEL, gbytes);
+    if (!d_rows) return RT_ERR_CUDA;
+    RT_CUDA(cudaMemsetAsync(d_rows, 0, gbytes, st));
+    if (n_sel > 0) {
+        int rc = rt_gram_rows_selected(d_ccol, d_cidx, d_cval, nnz, d_rptr, d_ridx, d_rval, d_slot, d_rows, ld, st);
+        if (rc) return rc;
+        rt::diag_from_rows_kernel<<<(I + 255) / 256, 256, 0, st>>>(d_slot, I, d_rows, ld, d_diag);
+        RT_CHECK_LAUNCH();
+    }
+    const void *bases[1] = {d_rows};
+    int rc = slim_solve_impl(nullptr, bases, 1, d_slot, d_diag, d_flag, ld, n_items, d_targets, n_targets, cfg, nullptr, d_rng, rng_len,
+                             nullptr, d_out_off, d_out_cnt, d_out_rows, d_out_vals, out_cap, h_needed, d_stats, stream);
+    if (rc == RT_OK || rc == RT_ERR_CAPACITY) *h_used = 1;
+    return rc;
 }

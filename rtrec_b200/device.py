@@ -329,6 +329,10 @@ def set_option(name: str, value: int) -> None:
     if name == "score_tc":
         _score_tc = int(value)
         return
+    if name == "fit_pruned":
+        global _fit_pruned
+        _fit_pruned = int(value)
+        return
     if name == "score_impl":
         _score_impl = int(value)
         if int(value) == 3:
@@ -392,6 +396,44 @@ def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool 
         break
     return SolveResult(targets, off, cnt, rows, vals, sel_out.view(T, nn) if sel_out is not None else None,
                        stats.view(-1, 4)[:T], nn == 0, int(needed.value))
+
+
+_fit_pruned = 1     # 0 = never use the pruned all-features fit (set_option("fit_pruned", 0))
+last_pruned_rows = None
+
+
+def fit_pruned(X: DeviceMatrix, targets, cfg: FitConfig) -> Optional[SolveResult]:
+    """All-features fit without the dense Gram matrix (rt_slim_fit_pruned): only the Gram rows of the items that can take
+    part in a non-zero solution are formed.  Returns the SolveResult of ``targets``, or None when the path does not apply
+    (feature selection, negative data, non-positive coefficients, or too many candidate rows): the caller then builds G."""
+    global last_pruned_rows
+    if not _fit_pruned or int(cfg.nn) != 0 or not cfg.positive or not cfg.nonneg or X.nnz == 0:
+        return None
+    t = require_cuda()
+    lib = _lib.load()
+    T = int(targets.numel())
+    if T == 0:
+        return None
+    I = X.n_items
+    rng = rng_table(int(cfg.seed), int(cfg.max_iter) * I + 64)
+    off = empty(T, t.int64); cnt = zeros(T, t.int32); stats = zeros(T * 4, t.int32)
+    cap = max(T * min(I, 256), 1024)
+    needed, used, n_rows = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+    while True:
+        rows = empty(cap, t.int32); vals = empty(cap, t.float32)
+        rc = lib.rt_slim_fit_pruned(X.n_users, I, ptr(X.cptr), ptr(X.cidx), ptr(X.cval), ptr(X.ccol), ptr(X.rptr), ptr(X.ridx),
+                                    ptr(X.rval), X.nnz, ptr(targets), T, C.byref(cfg), ptr(rng), rng.numel(), ptr(off), ptr(cnt),
+                                    ptr(rows), ptr(vals), cap, C.byref(needed), ptr(stats), C.byref(used), C.byref(n_rows),
+                                    stream_ptr())
+        if rc == _lib.RT_ERR_CAPACITY and needed.value > cap:
+            cap = int(needed.value)
+            continue
+        check(rc, "rt_slim_fit_pruned")
+        break
+    last_pruned_rows = int(n_rows.value)
+    if not used.value:
+        return None
+    return SolveResult(targets, off, cnt, rows, vals, None, stats.view(-1, 4), True, int(needed.value))
 
 
 def w_merge(old: Optional[DeviceW], n_items: int, res: SolveResult) -> DeviceW:

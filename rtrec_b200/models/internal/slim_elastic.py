@@ -140,7 +140,11 @@ class SLIMElastic:
         tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
         res = None
         ctx = self._dist_ctx()
-        if ctx is not None and X.nnz > 0 and sel_in is None:
+        if sel_in is None and int(cfg.nn) == 0:
+            # all features, positive coefficients, non-negative data: only the Gram rows that can matter are formed (every
+            # rank of an SPMD job does the same small fit: there is nothing worth sharding); None = path does not apply
+            res = D.fit_pruned(X, tg, cfg)
+        if res is None and ctx is not None and X.nnz > 0 and sel_in is None:
             # item-sharded fit: this rank solves the targets of its own Gram row blocks; the solver outputs (a few
             # MB) are all-gathered so that every rank assembles the same full W
             from ... import pipeline as P

@@ -76,7 +76,8 @@ def assert_w_parity(W_a, W_b, cols=None, max_flip_frac=0.02, what="W", X=None, a
     return rel
 
 
-def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-4, alpha=0.1, l1_ratio=0.1, tol=1e-4, what="W"):
+def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-4, alpha=0.1, l1_ratio=0.1, tol=1e-4, what="W",
+                             max_flip_frac=0.02):
     """Parity bar at the full ML-20M shape, where the reference's own float32 residual arithmetic is the limit.
 
     Measured with the CPU model of the device algorithm against the exact port of the reference on this shape
@@ -121,7 +122,7 @@ def assert_w_parity_at_scale(W_a, W_b, cols, X, big=1e-3, abs_tol=1e-4, alpha=0.
         ok, ratio = objectives_equal(j)
         report.append((j, scale, rel[j], ratio))
         assert ok, f"{what}: column {j} differs by {rel[j]:.3e} of {scale:.3e} and the objectives differ by {ratio:.3e} of tol*yy"
-    assert n_flip <= max(1, int(0.02 * max(n_big, 1))), f"{what}: {n_flip} of {n_big} columns with coefficients >= {big} above {W_TOL}"
+    assert n_flip <= max(1, int(max_flip_frac * max(n_big, 1))), f"{what}: {n_flip} of {n_big} columns with coefficients >= {big} above {W_TOL}"
     return rel, report
 
 

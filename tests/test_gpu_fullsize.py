@@ -59,6 +59,41 @@ def stratified_columns(W, Xc, rng, n_nontrivial=160, per_decile_any=12, among=No
     return np.unique(np.concatenate(picks)).astype(np.int32)
 
 
+def closer_to_float64_than_the_reference(W, Wo, Xo, cols, sel=None):
+    """For every column of ``cols``: the same sklearn solver in float64 on the same problem (column zeroed, optional
+    candidate list ``sel[t]``); the device column must be at least as close to it as the float32 oracle is (1.5x slack, or
+    within 1e-4 outright).  Returns the worst relative errors (device, oracle)."""
+    import warnings
+    from sklearn.linear_model import ElasticNet
+    U = Xo.shape[0]
+    X64 = Xo.astype(np.float64)
+    worst_dev, worst_ref = 0.0, 0.0
+    for t_, j in enumerate(cols):
+        a0, a1 = X64.indptr[j], X64.indptr[j + 1]
+        y = np.zeros(U); y[X64.indices[a0:a1]] = X64.data[a0:a1]
+        keep = X64.data[a0:a1].copy()
+        X64.data[a0:a1] = 0.0                                     # slim_elastic.py:266
+        en = ElasticNet(alpha=0.1, l1_ratio=0.1, fit_intercept=False, precompute=True, max_iter=100, copy_X=False, tol=1e-4,
+                        positive=True, random_state=43, selection="random")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if sel is None:
+                en.fit(X64, y)
+                w64 = en.coef_
+            else:
+                feats = sel[t_][sel[t_] >= 0]
+                en.fit(X64[:, feats], y)                          # slim_elastic.py:147
+                w64 = np.zeros(Xo.shape[1]); w64[feats] = en.coef_
+        X64.data[a0:a1] = keep
+        wd = np.asarray(W[:, j].todense()).ravel().astype(np.float64)
+        wr = np.asarray(Wo[:, j].todense()).ravel().astype(np.float64)
+        scale = max(np.abs(w64).max(), 1e-30)
+        e_dev, e_ref = np.abs(wd - w64).max() / scale, np.abs(wr - w64).max() / scale
+        worst_dev, worst_ref = max(worst_dev, e_dev), max(worst_ref, e_ref)
+        assert e_dev <= max(1e-4, 1.5 * e_ref), (int(j), e_dev, e_ref)
+    return worst_dev, worst_ref
+
+
 def device_sel(m, cols):
     pos = {int(t): k for k, t in enumerate(m.model.last_fit_targets)}
     return np.stack([m.model.last_fit_sel[pos[int(j)]] for j in cols])
@@ -261,8 +296,14 @@ def test_c3_hm_all_features_full_size(hm_events, hm_oracle_matrix):
     cols = np.unique(np.concatenate([cand, rng.choice(I, 64, replace=False)])).astype(np.int32)
     Wo = oracle_columns(Xo, cols, None)
     assert np.array_equal(np.flatnonzero(np.diff(Wo.indptr) > 0), nz_cols), "non-zero columns differ from the oracle's"
-    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, all features")
-    print(f"\n[c3 all] {len(cand)} candidate columns, {len(nz_cols)} non-zero, nnz(W) = {W.nnz}, worst column error {rel[cols].max():.3e}")
+    # At 1.37M samples the reference's own float32 residual arithmetic (sums of 1.4M fp32 terms per coordinate visit) is no
+    # longer good to 1e-4: every non-trivial column is a "flip" in the sense of tests/helpers.py (<= 1e-3, or equal
+    # objectives).  Which side is off is settled against a float64 run of the same sklearn solver on the same column: the
+    # device solution (fp64 solver state on the fp32 Gram matrix) must be at least as close to it as the float32 reference is.
+    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, all features", max_flip_frac=1.0)
+    worst_dev, worst_ref = closer_to_float64_than_the_reference(W, Wo, Xo, nz_cols[:8])
+    print(f"\n[c3 all] {len(cand)} candidate columns, {len(nz_cols)} non-zero, nnz(W) = {W.nnz}, worst column error vs the float32 "
+          f"oracle {rel[cols].max():.3e}; vs a float64 run of sklearn: device {worst_dev:.3e}, float32 oracle {worst_ref:.3e}")
     # ---- scoring for every user
     lists = m.recommend_batch(list(range(U)), top_k=10)
     keys = np.asarray(Xo.nonzero())
@@ -285,8 +326,12 @@ def test_c3_hm_nn50_full_size(hm_events, hm_oracle_matrix):
     rng = np.random.default_rng(4)
     cols = stratified_columns(W, Xo, rng, n_nontrivial=120, per_decile_any=4)
     Wo = oracle_columns(Xo, cols, 50, sel=device_sel(m, cols))
-    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, nn=50")
-    print(f"\n[c3 nn50] nnz(W) = {W.nnz}, {len(cols)} columns compared ({int((np.diff(W.indptr)[cols] > 0).sum())} non-trivial), worst {rel[cols].max():.3e}")
+    # (every non-trivial column is a "flip" against the float32 oracle at 1.37M samples, see the all-features test)
+    rel, _ = assert_w_parity_at_scale(W, Wo, cols, Xo, what="W at H&M shape, nn=50", max_flip_frac=1.0)
+    nt = [k_ for k_, j in enumerate(cols) if W.indptr[j + 1] > W.indptr[j]][:8]
+    worst_dev, worst_ref = closer_to_float64_than_the_reference(W, Wo, Xo, cols[nt], sel=device_sel(m, cols[nt]))
+    print(f"\n[c3 nn50] nnz(W) = {W.nnz}, {len(cols)} columns compared ({int((np.diff(W.indptr)[cols] > 0).sum())} non-trivial), worst "
+          f"{rel[cols].max():.3e} vs the float32 oracle; vs float64 sklearn: device {worst_dev:.3e}, float32 oracle {worst_ref:.3e}")
     lists = m.recommend_batch(list(range(U)), top_k=10)
     keys = np.asarray(Xo.nonzero())
     lens, _ = check_lists(lists, keys[0], keys[1], U, I)

@@ -360,6 +360,44 @@ def test_tensor_core_scoring_matches_exact_scores(rating):
         D.set_option("score_tc", 1)
 
 
+def test_pruned_all_features_fit_equals_dense_path():
+    """rt_slim_fit_pruned: all-features fit from the Gram rows of the Cauchy-Schwarz candidates only.  Same W as the dense
+    path (Gram entries are accumulated by a different kernel: agreement to float32 rounding, same non-zero pattern), same
+    stats for the zero columns, far fewer Gram rows; falls back (None) when the candidates are most of the catalogue."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    U, I, N = 60000, 2500, 300000
+    u, i, ts, r = synth_events(U, I, N, seed=13, rating="cont")           # a = 0.01 * 60000 = 600: few live coordinates
+    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    dX = D.DeviceMatrix.from_scipy(X)
+    op = SLIMElastic({})
+    cfg = op._config(dX)
+    tg = torch.arange(I, dtype=torch.int32, device="cuda")
+    res_p = D.fit_pruned(dX, tg, cfg)
+    assert res_p is not None and 0 < D.last_pruned_rows <= I // 4, D.last_pruned_rows
+    Wp = D.w_merge(None, I, res_p).to_scipy_csc()
+    G = D.gram_full(dX)
+    res_d = D.solve(G, I, tg, cfg)
+    Wd = D.w_merge(None, I, res_d).to_scipy_csc()
+    assert Wd.nnz > 0
+    assert np.array_equal(Wp.indptr, Wd.indptr) and np.array_equal(Wp.indices, Wd.indices)
+    assert np.abs(Wp.data - Wd.data).max() <= 1e-4 * np.abs(Wd.data).max()
+    sp_, sd = res_p.stats.cpu().numpy(), res_d.stats.cpu().numpy()
+    triv = sd[:, 3] == 0
+    assert np.array_equal(sp_[triv], sd[triv])
+    # every non-zero column lies inside the candidate set, and the operator takes this path by itself
+    op.fit(dX)
+    assert (op.item_similarity != Wp).nnz == 0
+    # a small threshold (few users): most items are candidates -> the dense path is the better one
+    u2, i2, ts2, r2 = synth_events(400, 300, 9000, seed=14, rating="cont")
+    dX2 = D.DeviceMatrix.from_scipy(sp.csc_matrix((r2.astype(np.float32), (u2, i2)), shape=(400, 300)))
+    assert D.fit_pruned(dX2, torch.arange(300, dtype=torch.int32, device="cuda"), op._config(dX2)) is None
+    assert D.last_pruned_rows > 300 // 4
+    # feature selection is not this path's business
+    assert D.fit_pruned(dX, tg, SLIMElastic({"nn_feature_selection": 20})._config(dX)) is None
+
+
 @pytest.mark.parametrize("nn", [20, None])
 def test_trivial_columns_shortcut_gives_the_same_w(nn):
     """Targets whose Gram row has no entry above the L1 threshold are zero before the first sweep.  Bulk fits return them
