@@ -368,8 +368,10 @@ def test_pruned_all_features_fit_equals_dense_path():
     from rtrec_b200 import device as D
     from rtrec_b200.models.internal.slim_elastic import SLIMElastic
     U, I, N = 60000, 2500, 300000
-    u, i, ts, r = synth_events(U, I, N, seed=13, rating="cont")           # a = 0.01 * 60000 = 600: few live coordinates
-    X = sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I))
+    u, i, ts, r = synth_events(U, I, N, seed=13, rating="cont")
+    # small values (as after a time decay): a = 0.01 * 60000 = 600 is above most Gram entries, and the Cauchy-Schwarz
+    # bound d_j * d_max > a^2 only holds for the few dozen most popular items
+    X = sp.csc_matrix(((0.2 * r).astype(np.float32), (u, i)), shape=(U, I))     # 301 candidates, 7 non-trivial columns
     dX = D.DeviceMatrix.from_scipy(X)
     op = SLIMElastic({})
     cfg = op._config(dX)
