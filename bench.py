@@ -487,8 +487,9 @@ def fit_phases(c, args, X, op, mark):
     cfg = op._config(X)
     rank, world = c.rank, c.world
     res = None
-    if int(cfg.nn) == 0:
-        # all features: only the Gram rows that can carry a non-zero solution (every rank does this small fit itself)
+    if int(cfg.nn) == 0 or cfg.skip_trivial:
+        # only the Gram rows that can carry a non-zero solution, when they are few (Cauchy-Schwarz bound; every rank does
+        # this small fit itself); None = most of the catalogue qualifies (ML-20M shape): the dense / owner-rows path below
         res = D.fit_pruned(X, t.arange(X.n_items, dtype=t.int32, device="cuda"), cfg)
         if res is not None:
             mark("fit_pruned")

@@ -171,6 +171,12 @@ int rt_gram_lower(int32_t n_users, int32_t n_items, const int32_t *d_cptr, const
 int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
                    const int32_t *d_orig_of, float *d_G, int64_t ldg, void *stream);
 
+/* rt_gram_finish that also writes d_rowmax[i] = max_{c != i} G[i][c] (float[n_items], by item id) while the rows pass
+ * through shared memory; *h_has_rowmax = 0 when the rows are too long to be staged (d_rowmax is then left untouched). */
+int rt_gram_finish_rowmax(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                          const int32_t *d_orig_of, float *d_G, int64_t ldg, float *d_rowmax,
+                          int32_t *h_has_rowmax, void *stream);
+
 /*
  * Multi-GPU form of rt_gram_finish: the slab exchange is fused with the mirror step over peer memory.
  * h_slabs[p] (HOST array of n_parts DEVICE pointers, p = part index) addresses the d_Gp buffer of rank p
@@ -257,6 +263,9 @@ typedef struct {
     int32_t nn;          /* nn_feature_selection (:190), 0 = all items are features */
     int32_t n_samples;   /* rows of X = max_user_id+1; scales the penalties (_coordinate_descent.py:781) */
     int32_t nonneg;      /* 1 iff every stored value of X is >= 0 (enables live-set pruning) */
+    uint64_t rowmax_ptr;  /* optional DEVICE pointer (0 = none) to float[n_items]: the largest off-diagonal Gram entry of every
+                            item's row, as rt_gram_finish_rowmax writes it.  With skip_trivial the warp solver then finishes a
+                            target without a live coordinate without reading its Gram row at all. */
     int32_t skip_trivial; /* 1: with feature selection (nn > 0), a target whose Gram row holds no entry above
                             alpha*l1_ratio*n_samples -- all nn coefficients are 0 before the first sweep -- may be returned
                             with NO pairs (d_out_cnt = 0) instead of nn zeros, and its candidates are not selected.  Valid
@@ -307,8 +316,9 @@ int rt_slim_solve_rows(const void *const *h_bases, int32_t n_bases, const int32_
                        int64_t out_cap, int64_t *h_needed, int32_t *d_stats, void *stream);
 
 /*
- * All-features fit (nn == 0) with positive coefficients on non-negative data WITHOUT the dense Gram matrix (same result
- * contract as rt_gram_lower + rt_gram_finish + rt_slim_solve; replaces slim_elastic.py:229-281 for that configuration).
+ * Fit with positive coefficients on non-negative data WITHOUT the dense Gram matrix -- all features (nn == 0), or feature
+ * selection in a bulk fit (cfg->skip_trivial) -- with the same result contract as rt_gram_lower + rt_gram_finish +
+ * rt_slim_solve (replaces slim_elastic.py:229-281 for those configurations).
  * A coordinate c of target j can only leave 0 if G[j][c] > alpha*l1_ratio*n_samples, and G[j][c] <= sqrt(G[j][j] G[c][c]):
  * one pass over X (column sums of squares) names the items that can take part in any non-zero solution; only their Gram
  * rows are formed (library scratch, n_rows x n_items floats) and only they are solved, every other target is returned

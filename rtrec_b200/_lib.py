@@ -37,6 +37,7 @@ class FitConfig(C.Structure):
         ("nn", C.c_int32),
         ("n_samples", C.c_int32),
         ("nonneg", C.c_int32),
+        ("rowmax_ptr", C.c_uint64),
         ("skip_trivial", C.c_int32),
     ]
 
@@ -64,6 +65,7 @@ PROTOTYPES = {
     "rt_gram": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I64, _P]),
     "rt_gram_lower": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, C.POINTER(_I32), _P]),
     "rt_gram_finish": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P]),
+    "rt_gram_finish_rowmax": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P, C.POINTER(_I32), _P]),
     "rt_gram_block_rows": (C.c_int, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "rt_gram_lower_blocks": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
     "rt_gram_pull_cols": (C.c_int, [_I32, _P, _I32, _I32, _I64, _P]),

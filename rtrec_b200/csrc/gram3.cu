@@ -81,6 +81,116 @@ __global__ void pack_entries_kernel(const int *__restrict__ pidx, const float *_
     pent[i] = make_int2(rank - g * RW, __float_as_int(pval[i]));
 }
 
+// ---- rank-sorted CSR by a segmented sort -----------------------------------------------------------------------------
+// The Gram kernel wants every user's row ordered by the popularity rank of its items.  The rows are already contiguous
+// (CSR), so this is a sort WITHIN each row -- not the two global radix sorts (rank bits, then user bits: five passes over
+// 12-byte pairs) of the first version.  Rows of at most 64 entries are sorted by one warp in registers (two entries per
+// lane, bitonic network over shuffles), longer rows by one CTA in shared memory (bitonic, up to RS_BIG entries); ranks
+// within a row are distinct, so no stability question arises.  Rows longer than RS_BIG send the whole matrix down the
+// radix path (the launcher knows the longest row).
+constexpr int RS_BIG = 8192;
+constexpr int RS_NT = 256;
+
+__device__ __forceinline__ void rs_cx(int &ka, float &va, int &kb, float &vb, bool up) {   // compare-exchange two entries
+    if ((ka > kb) == up) { const int t = ka; ka = kb; kb = t; const float f = va; va = vb; vb = f; }
+}
+
+__global__ void __launch_bounds__(256) row_sort_small_kernel(int n_users, const int *__restrict__ rptr, const int *__restrict__ ridx,
+                                                             const float *__restrict__ rval, const int *__restrict__ rank_of,
+                                                             int *__restrict__ pidx, float *__restrict__ pval) {
+    const int lane = threadIdx.x & 31;
+    const int u = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (u >= n_users) return;
+    const int a = rptr[u], n = rptr[u + 1] - a;
+    if (n == 0 || n > 64) return;
+    // element e of the network lives in lane e & 31, slot e >> 5; padding sorts to the end
+    int k0 = 0x7fffffff, k1 = 0x7fffffff;
+    float v0 = 0.f, v1 = 0.f;
+    if (lane < n) { k0 = rank_of[ridx[a + lane]]; v0 = rval[a + lane]; }
+    if (lane + 32 < n) { k1 = rank_of[ridx[a + lane + 32]]; v1 = rval[a + lane + 32]; }
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32) {
+                // partner of element e is e ^ 32: the other slot of the same lane; direction from bit `size` of e (size = 64: up)
+                rs_cx(k0, v0, k1, v1, true);
+            } else {
+                // both slots exchange with lane ^ stride
+#pragma unroll
+                for (int slot = 0; slot < 2; ++slot) {
+                    int &k = slot ? k1 : k0;
+                    float &v = slot ? v1 : v0;
+                    const int e = lane + 32 * slot;
+                    const int ok = __shfl_xor_sync(0xffffffffu, k, stride);
+                    const float ov = __shfl_xor_sync(0xffffffffu, v, stride);
+                    const bool up = (e & size) == 0;             // ascending block?
+                    const bool lower = (e & stride) == 0;        // this element is the lower one of its pair
+                    const bool take = lower ? ((k > ok) == up) : ((ok > k) == up);
+                    if (take) { k = ok; v = ov; }
+                }
+            }
+        }
+    }
+    if (lane < n) { pidx[a + lane] = k0; pval[a + lane] = v0; }
+    if (lane + 32 < n) { pidx[a + lane + 32] = k1; pval[a + lane + 32] = v1; }
+}
+
+__global__ void __launch_bounds__(RS_NT) row_sort_big_kernel(int n_users, const int *__restrict__ rptr, const int *__restrict__ ridx,
+                                                            const float *__restrict__ rval, const int *__restrict__ rank_of,
+                                                            int *__restrict__ pidx, float *__restrict__ pval,
+                                                            int *__restrict__ next_row) {
+    extern __shared__ __align__(16) int rs_smem[];     // keys[RS_BIG], then values[RS_BIG]
+    int *sk = rs_smem;
+    float *sv = reinterpret_cast<float *>(rs_smem + RS_BIG);
+    __shared__ int s_u;
+    const int tid = threadIdx.x;
+    for (;;) {
+        // rows are claimed 64 at a time; short rows (the warp kernel's) are skipped
+        __syncthreads();
+        if (tid == 0) s_u = atomicAdd(next_row, 64);
+        __syncthreads();
+        const int u0 = s_u;
+        if (u0 >= n_users) break;
+        for (int u = u0; u < min(u0 + 64, n_users); ++u) {
+            const int a = rptr[u], n = rptr[u + 1] - a;
+            if (n <= 64) continue;                              // (uniform: every thread reads the same rptr)
+            int np = 128;
+            while (np < n) np <<= 1;
+            __syncthreads();
+            for (int e = tid; e < np; e += RS_NT) {
+                if (e < n) { sk[e] = rank_of[ridx[a + e]]; sv[e] = rval[a + e]; }
+                else { sk[e] = 0x7fffffff; sv[e] = 0.f; }
+            }
+            __syncthreads();
+            for (int size = 2; size <= np; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = tid; t < (np >> 1); t += RS_NT) {
+                        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                        const int hi = lo | stride;
+                        const bool up = (lo & size) == 0;
+                        const int ka = sk[lo], kb = sk[hi];
+                        if ((ka > kb) == up) {
+                            sk[lo] = kb; sk[hi] = ka;
+                            const float f = sv[lo]; sv[lo] = sv[hi]; sv[hi] = f;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int e = tid; e < n; e += RS_NT) { pidx[a + e] = sk[e]; pval[a + e] = sv[e]; }
+        }
+    }
+}
+
+__global__ void max_row_len_kernel(int n_users, const int *__restrict__ rptr, int *__restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = u < n_users ? rptr[u + 1] - rptr[u] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
 // one thread per stored entry e = (u, j): position of rank(j) inside the rank-sorted row of u; optionally
 // the exact multiply-add count of every rank-column (sum of prefix lengths) for the multi-GPU partition
 __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict__ rank_of, const int *__restrict__ cptr,
@@ -409,17 +519,33 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, f
 // back to item ids and rows are addressed through rt_gram_row_slots)
 __global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n_rows, int n,
                                                               const int *__restrict__ rank_of, const int *__restrict__ orig_of,
-                                                              float *__restrict__ G, int64_t ld, int stage) {
+                                                              float *__restrict__ G, int64_t ld, int stage,
+                                                              float *__restrict__ rowmax) {
+    // rowmax (optional, staged mode with orig_of): largest off-diagonal entry of every row, by item id -- the solver uses it
+    // to finish targets without a live coordinate without reading their Gram rows again
     extern __shared__ __align__(16) float row_s[];
+    __shared__ float s_red[32];
     const int NT = blockDim.x;
     for (int jp = blockIdx.x; jp < n_rows; jp += gridDim.x) {
         const float *src = Gp + (size_t)jp * ldp;
         float *dst = G + (size_t)(orig_of ? orig_of[jp] : jp) * ld;
         if (stage) {
             __syncthreads();
+            float mx = -INFINITY;
 #pragma unroll 4
-            for (int x = threadIdx.x; x < n; x += NT) row_s[x] = src[x];
+            for (int x = threadIdx.x; x < n; x += NT) { const float v = src[x]; row_s[x] = v; if (x != jp) mx = fmaxf(mx, v); }
+            if (rowmax && orig_of) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+            }
             __syncthreads();
+            if (rowmax && orig_of && threadIdx.x < 32) {
+                float m2 = threadIdx.x < (NT >> 5) ? s_red[threadIdx.x] : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+                if (threadIdx.x == 0) rowmax[orig_of[jp]] = m2;
+            }
 #pragma unroll 4
             for (int x = threadIdx.x; x < n; x += NT) dst[x] = row_s[rank_of[x]];
         } else {
@@ -563,7 +689,29 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
     if (nnz == 0) { RT_CUDA(cudaStreamSynchronize(st)); return RT_OK; }
     RT_ARG(d_cidx && d_cval && d_ridx && d_rval, "null pointer");
     // ---- rank-sorted CSR ---------------------------------------------------------------------------
+    int max_len = 0;
     {
+        int *d_max = (int *)P.counter + 2;      // (counter[0] is the task cursor of the lower-triangle kernel)
+        RT_CUDA(cudaMemsetAsync(P.counter, 0, 4 * sizeof(unsigned long long), st));
+        max_row_len_kernel<<<(n_users + bs - 1) / bs, bs, 0, st>>>(n_users, d_rptr, d_max);
+        RT_CHECK_LAUNCH();
+        RT_CUDA(cudaMemcpyAsync(&max_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RT_CUDA(cudaStreamSynchronize(st));
+    }
+    if (max_len <= RS_BIG && rt::option(rt::OPT_GRAM_IMPL) != 1) {
+        // segmented sort: every row by the rank of its items (warp kernel for rows <= 64, CTA kernel for the rest)
+        row_sort_small_kernel<<<(unsigned)(((int64_t)n_users * 32 + bs - 1) / bs), bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rval,
+                                                                                            d_rank_of, P.pidx, P.pval);
+        RT_CHECK_LAUNCH();
+        if (max_len > 64) {
+            int *d_next = (int *)P.counter + 4;
+            const size_t smem = (size_t)RS_BIG * 8;
+            RT_CUDA(cudaFuncSetAttribute(row_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            row_sort_big_kernel<<<rt::sm_count() * 3, RS_NT, smem, st>>>(n_users, d_rptr, d_ridx, d_rval, d_rank_of, P.pidx, P.pval,
+                                                                       d_next);
+            RT_CHECK_LAUNCH();
+        }
+    } else {
         const unsigned grid = (unsigned)(((int64_t)n_users * 32 + bs - 1) / bs);
         relabel_keys_kernel<<<grid, bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rank_of, P.keys);
         RT_CHECK_LAUNCH();
@@ -664,7 +812,8 @@ extern "C" int rt_gram_lower_blocks(int32_t n_users, int32_t n_items, const int3
 }
 
 static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
-                            const int32_t *d_orig_of, float *d_G, int64_t ldg, cudaStream_t st) {
+                            const int32_t *d_orig_of, float *d_G, int64_t ldg, cudaStream_t st, float *d_rowmax = nullptr,
+                            int32_t *h_has_rowmax = nullptr) {
     const size_t row_bytes = sizeof(float) * (size_t)n_items;
     const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
     const size_t smem = stage ? row_bytes : 0;
@@ -674,8 +823,10 @@ static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, co
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_items) grid = n_items;
-    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, n_items, d_rank_of, d_orig_of, d_G, ldg, stage);
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, n_items, d_rank_of, d_orig_of, d_G, ldg, stage,
+                                                    stage ? d_rowmax : nullptr);
     RT_CHECK_LAUNCH();
+    if (h_has_rowmax) *h_has_rowmax = (stage && d_rowmax) ? 1 : 0;
     return RT_OK;
 }
 
@@ -724,7 +875,7 @@ extern "C" int rt_gram_unpermute_rows(int32_t n_rows, int32_t n_items, const flo
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_rows) grid = n_rows;
-    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_slab, ldgp, n_rows, n_items, d_rank_of, nullptr, d_rows, ldg, stage);
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_slab, ldgp, n_rows, n_items, d_rank_of, nullptr, d_rows, ldg, stage, nullptr);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }
@@ -778,4 +929,16 @@ extern "C" int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const 
     gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
     RT_CHECK_LAUNCH();
     return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
+}
+
+extern "C" int rt_gram_finish_rowmax(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                                     const int32_t *d_orig_of, float *d_G, int64_t ldg, float *d_rowmax,
+                                     int32_t *h_has_rowmax, void *stream) {
+    RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items && d_rowmax && h_has_rowmax, "arguments");
+    RT_ARG(d_Gp != d_G, "rt_gram_finish is not in-place");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nt = (n_items + 31) / 32;
+    gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
+    RT_CHECK_LAUNCH();
+    return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st, d_rowmax, h_has_rowmax);
 }

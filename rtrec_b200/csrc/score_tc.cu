@@ -422,6 +422,7 @@ struct FxShared {
     int la[FX_ROWS];     // staged light rows: first entry in W's CSR, exclusive prefix of the lengths, rating
     int lpre[FX_ROWS + 1];
     float lx[FX_ROWS];
+    unsigned long long staged;   // high word: staged rows, low word: their entries (one atomic claims a slot AND its offset)
     int n_rows;
     int hh[TC_KH];
     float hx[TC_KH];
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
             for (int s = tid; s < FX_SLOTS / 4; s += FX_NT) kv[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             for (int s = tid; s < FX_SLOTS / 2; s += FX_NT) vv[s] = make_uint4(0u, 0u, 0u, 0u);
         }
-        if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; S.n_rows = 0; }
+        if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; S.n_rows = 0; S.staged = 0ull; }
         __syncthreads();
         // ---- pass 1: one coalesced sweep over the row: heavy items (ascending, ordered compaction) and the light rows
         // (first entry, length, rating) staged in shared memory -- the scatter below then has no dependent global loads
@@ -475,8 +476,10 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
                 if (h < 0) { a = wrptr[i]; len = wrptr[i + 1] - a; }
             }
             if (len > 0) {
-                const int slot = atomicAdd(&S.n_rows, 1);
-                if (slot < FX_ROWS) { S.la[slot] = a; S.lpre[slot] = len; S.lx[slot] = x; }
+                // slot and exclusive entry offset from ONE atomic, so the offsets ascend with the slots (binary-searchable)
+                const unsigned long long old = atomicAdd(&S.staged, (1ull << 32) | (unsigned long long)(unsigned)len);
+                const int slot = (int)(old >> 32);
+                if (slot < FX_ROWS) { S.la[slot] = a; S.lpre[slot] = (int)(old & 0xffffffffull); S.lx[slot] = x; }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, h >= 0);
             if (lane == 0) S.red_i[warp] = __popc(bal);
@@ -488,25 +491,12 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
             if (tid == 0) S.n_heavy_u += tot;
             __syncthreads();
         }
-        const int n_rows = S.n_rows;
+        const int n_rows = (int)(S.staged >> 32);
         if (n_rows > FX_ROWS) {         // more light items than can be staged: the exact kernel scores this user
             if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
             continue;
         }
-        // exclusive prefix of the staged lengths (one warp, 32 rows per step)
-        if (warp == 0) {
-            int run = 0;
-            for (int b0 = 0; b0 < n_rows; b0 += 32) {
-                const int r = b0 + lane;
-                const int len = r < n_rows ? S.lpre[r] : 0;
-                int inc = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t_ = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t_; }
-                if (r < n_rows) S.lpre[r] = run + inc - len;
-                run += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            if (lane == 0) { S.lpre[n_rows] = run; S.n_light = run; }
-        }
+        if (tid == 0) { S.lpre[n_rows] = (int)(S.staged & 0xffffffffull); S.n_light = (int)(S.staged & 0xffffffffull); }
         __syncthreads();
         const int n_light = S.n_light;
         if (n_light > FX_CAP) {      // the table would overflow: the exact kernel scores this user

@@ -51,6 +51,7 @@ struct SolveArgs {
     const int *only_flagged;  // when set, the block kernel solves only targets t with only_flagged[t] != 0
     int flag_mod;             // test hook (solve_impl = 3): the warp kernel hands every flag_mod-th target to the block kernel
     int skip_trivial;  // nn mode: targets without a live coordinate return no pairs (rt_fit_config.skip_trivial)
+    const float *rowmax;   // optional: largest off-diagonal Gram entry per item (rt_fit_config.rowmax_ptr)
     const int *item_flag;  // pruned fit: items whose Gram row exists (others are trivial targets and are never dereferenced)
     int hit_mode;      // all-features mode: shared-memory bitmap of the live positions of active[] + per-sweep hit lists
     int bm_off;        // byte offset of the bitmap in dynamic shared memory (hit_mode)
@@ -152,6 +153,13 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 8 : 2) slim_solve_kernel(S
         if (t >= A.n_targets) break;
         if (A.only_flagged && !A.only_flagged[t]) continue;
         const int j = A.targets[t];
+        if (nnmode && A.skip_trivial && A.item_flag && !A.item_flag[j]) {     // pruned fit: no row, zero column
+            if (tid == 0) {
+                A.out_off[t] = (int64_t)t * NU; A.out_cnt[t] = 0;
+                if (A.stats) { A.stats[(size_t)t * 4 + 0] = 0; A.stats[(size_t)t * 4 + 1] = 0; A.stats[(size_t)t * 4 + 2] = 1; A.stats[(size_t)t * 4 + 3] = 0; }
+            }
+            continue;
+        }
         const float *gj = g_row(A, j);
 
         // ---- universe ------------------------------------------------------------------------
@@ -209,9 +217,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 8 : 2) slim_solve_kernel(S
             }
             __syncthreads();
         }
-        // G entry between two live slots
+        // G entry between two live slots.  Without the shared-memory block the callers sweep sr for a fixed sc: by symmetry
+        // (rt_gram_finish writes G[a][b] == G[b][a] bit for bit) the entry is read from ROW sc at column live[sr], so that the
+        // threads of a warp gather ascending positions of ONE row instead of one cache line from each of m rows
         auto GL = [&](int sr, int sc) -> double {
-            return A.use_gs ? (double)Gs[sr * m + sc] : (double)g_row(A, F(live[sr]))[F(live[sc])];
+            return A.use_gs ? (double)Gs[sr * m + sc] : (double)g_row(A, F(live[sc]))[F(live[sr])];
         };
 
         int n_active = 0, n_iter = 0, n_gap = 0, draws = 0;
@@ -562,6 +572,15 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= A.n_targets) break;
         const int j = A.targets[t];
+        if (A.skip_trivial && ((A.rowmax && !((double)A.rowmax[j] > a)) || (A.item_flag && !A.item_flag[j]))) {
+            // no entry of the Gram row is above the L1 threshold (known from rt_gram_finish_rowmax, or the item is not a
+            // Cauchy-Schwarz candidate of the pruned fit and has no row): the zero column, and the row is not even read
+            if (lane == 0) {
+                A.out_off[t] = (int64_t)t * NU; A.out_cnt[t] = 0;
+                if (A.stats) { A.stats[(size_t)t * 4 + 0] = 0; A.stats[(size_t)t * 4 + 1] = 0; A.stats[(size_t)t * 4 + 2] = 1; A.stats[(size_t)t * 4 + 3] = 0; }
+            }
+            continue;
+        }
         const float *gj = g_row(A, j);
         __syncwarp();
 
@@ -791,20 +810,21 @@ __global__ void __launch_bounds__(512, 1) slim_solve_warp_kernel(SolveArgs A, in
                     const int f = S->feat[k];
                     if (f == j) v = 0.0;
                     else {
-                        // row f of the symmetric G at the support columns: ns independent loads, four in flight
-                        const float *gf = g_row(A, f);
+                        // G[support][f] for the support coordinates: ns independent loads, four in flight.  The entry is read
+                        // from the SUPPORT item's row (G is symmetric): support items are live, so their rows exist in the
+                        // pruned fit, where the row of a non-live candidate f may not
                         double hk = 0.0;
                         int e = 0;
                         for (; e + 3 < ns; e += 4) {
                             const int s0 = S->list[e], s1 = S->list[e + 1], s2 = S->list[e + 2], s3 = S->list[e + 3];
-                            const float g0 = __ldg(gf + S->feat[S->live[s0]]), g1 = __ldg(gf + S->feat[S->live[s1]]);
-                            const float g2 = __ldg(gf + S->feat[S->live[s2]]), g3 = __ldg(gf + S->feat[S->live[s3]]);
+                            const float g0 = __ldg(g_row(A, S->feat[S->live[s0]]) + f), g1 = __ldg(g_row(A, S->feat[S->live[s1]]) + f);
+                            const float g2 = __ldg(g_row(A, S->feat[S->live[s2]]) + f), g3 = __ldg(g_row(A, S->feat[S->live[s3]]) + f);
                             hk += (double)g0 * S->w[s0]; hk += (double)g1 * S->w[s1];
                             hk += (double)g2 * S->w[s2]; hk += (double)g3 * S->w[s3];
                         }
                         for (; e < ns; ++e) {
                             const int sc = S->list[e];
-                            hk += (double)__ldg(gf + S->feat[S->live[sc]]) * S->w[sc];
+                            hk += (double)__ldg(g_row(A, S->feat[S->live[sc]]) + f) * S->w[sc];
                         }
                         v = (double)gj[f] - hk;
                     }
@@ -1137,6 +1157,7 @@ static int slim_solve_impl(const float *d_G, const void *const *h_bases, int32_t
     A.hit_mode = rt::option(rt::OPT_SOLVE_IMPL) == 1 ? 0 : p.hit_mode; A.bm_off = p.bm_off;
     A.only_flagged = nullptr;
     A.item_flag = d_item_flag;
+    A.rowmax = (d_G && cfg->rowmax_ptr) ? reinterpret_cast<const float *>((uintptr_t)cfg->rowmax_ptr) : nullptr;
     A.skip_trivial = (cfg->nn > 0 && cfg->skip_trivial && cfg->positive && cfg->nonneg && !d_sel_out && !d_sel_in) ? 1 : 0;
     A.flag_mod = rt::option(rt::OPT_SOLVE_IMPL) == 3 ? 7 : 0;
     RT_CUDA(cudaMemsetAsync(d_workspace, 0, 1024, st));
@@ -1319,7 +1340,8 @@ extern "C" int rt_slim_fit_pruned(int32_t n_users, int32_t n_items, const int32_
     RT_ARG(cfg && h_used && h_n_rows, "cfg / outputs");
     *h_used = 0; *h_n_rows = 0;
     if (h_needed) *h_needed = 0;
-    if (!(cfg->nn == 0 && cfg->positive && cfg->nonneg) || nnz <= 0 || n_targets <= 0) return RT_OK;   // not applicable
+    // all features, or feature selection in a bulk fit (skip_trivial: columns without a live coordinate may come back empty)
+    if (!((cfg->nn == 0 || cfg->skip_trivial) && cfg->positive && cfg->nonneg) || nnz <= 0 || n_targets <= 0) return RT_OK;
     RT_ARG(n_users > 0 && n_items > 0 && n_items < (1 << 24) && d_cptr && d_cidx && d_cval && d_ccol && d_rptr && d_ridx && d_rval &&
                d_targets, "matrix arguments");
     cudaStream_t st = (cudaStream_t)stream;

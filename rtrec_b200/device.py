@@ -301,8 +301,13 @@ def gram_finish(L: GramLower, out=None):
     I = L.Gp.shape[0]
     if out is None:
         out = t.empty((I, I), dtype=t.float32, device=dev())
-    check(_lib.load().rt_gram_finish(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, stream_ptr()),
-          "rt_gram_finish")
+    # the rows pass through shared memory on their way back to item ids: their largest off-diagonal entry comes for free
+    # and rides along on the tensor (``solve`` hands it to the solver, which then skips trivial targets without a read)
+    rowmax = empty(I, t.float32)
+    has = C.c_int32(0)
+    check(_lib.load().rt_gram_finish_rowmax(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, ptr(rowmax),
+                                            C.byref(has), stream_ptr()), "rt_gram_finish_rowmax")
+    out._rt_rowmax = rowmax if has.value else None
     return out
 
 
@@ -386,6 +391,10 @@ def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool 
                                         ptr(sel_in), ptr(rng), rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows),
                                         ptr(vals), cap, C.byref(needed), ptr(stats), stream_ptr())
         else:
+            rowmax = getattr(G, "_rt_rowmax", None)
+            if rowmax is not None and not cfg.rowmax_ptr:
+                cfg = FitConfig.from_buffer_copy(cfg)
+                cfg.rowmax_ptr = rowmax.data_ptr()
             rc = lib.rt_slim_solve(ptr(G), G.stride(0), n_items, ptr(targets), T, C.byref(cfg), ptr(sel_in), ptr(rng),
                                    rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows), ptr(vals), cap, C.byref(needed),
                                    ptr(stats), stream_ptr())
@@ -403,11 +412,13 @@ last_pruned_rows = None
 
 
 def fit_pruned(X: DeviceMatrix, targets, cfg: FitConfig) -> Optional[SolveResult]:
-    """All-features fit without the dense Gram matrix (rt_slim_fit_pruned): only the Gram rows of the items that can take
-    part in a non-zero solution are formed.  Returns the SolveResult of ``targets``, or None when the path does not apply
-    (feature selection, negative data, non-positive coefficients, or too many candidate rows): the caller then builds G."""
+    """Fit without the dense Gram matrix (rt_slim_fit_pruned): only the Gram rows of the items that can take part in a
+    non-zero solution are formed.  Applies to all-features fits and to bulk fits with feature selection
+    (``cfg.skip_trivial``).  Returns the SolveResult of ``targets``, or None when the path does not apply (negative data,
+    non-positive coefficients, a merge into an existing W with feature selection, or too many candidate rows): the
+    caller then builds G."""
     global last_pruned_rows
-    if not _fit_pruned or int(cfg.nn) != 0 or not cfg.positive or not cfg.nonneg or X.nnz == 0:
+    if not _fit_pruned or not cfg.positive or not cfg.nonneg or X.nnz == 0 or (int(cfg.nn) != 0 and not cfg.skip_trivial):
         return None
     t = require_cuda()
     lib = _lib.load()
@@ -415,9 +426,11 @@ def fit_pruned(X: DeviceMatrix, targets, cfg: FitConfig) -> Optional[SolveResult
     if T == 0:
         return None
     I = X.n_items
-    rng = rng_table(int(cfg.seed), int(cfg.max_iter) * I + 64)
+    nn = int(cfg.nn)
+    NU = min(nn, I) if nn > 0 else I
+    rng = rng_table(int(cfg.seed), int(cfg.max_iter) * NU + 64)
     off = empty(T, t.int64); cnt = zeros(T, t.int32); stats = zeros(T * 4, t.int32)
-    cap = max(T * min(I, 256), 1024)
+    cap = T * NU if nn > 0 else max(T * min(I, 256), 1024)
     needed, used, n_rows = C.c_int64(0), C.c_int32(0), C.c_int32(0)
     while True:
         rows = empty(cap, t.int32); vals = empty(cap, t.float32)
@@ -433,7 +446,7 @@ def fit_pruned(X: DeviceMatrix, targets, cfg: FitConfig) -> Optional[SolveResult
     last_pruned_rows = int(n_rows.value)
     if not used.value:
         return None
-    return SolveResult(targets, off, cnt, rows, vals, None, stats.view(-1, 4), True, int(needed.value))
+    return SolveResult(targets, off, cnt, rows, vals, None, stats.view(-1, 4), nn == 0, int(needed.value))
 
 
 def w_merge(old: Optional[DeviceW], n_items: int, res: SolveResult) -> DeviceW:

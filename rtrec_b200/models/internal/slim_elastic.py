@@ -140,9 +140,10 @@ class SLIMElastic:
         tg = D.to_dev(np.ascontiguousarray(targets, dtype=np.int32))
         res = None
         ctx = self._dist_ctx()
-        if sel_in is None and int(cfg.nn) == 0:
-            # all features, positive coefficients, non-negative data: only the Gram rows that can matter are formed (every
-            # rank of an SPMD job does the same small fit: there is nothing worth sharding); None = path does not apply
+        if sel_in is None and not self.keep_fit_details:
+            # positive coefficients on non-negative data (all features, or a bulk fit with feature selection): only the Gram
+            # rows that can matter are formed when they are few (every rank of an SPMD job does the same small fit: there is
+            # nothing worth sharding); None = path does not apply / not worth it
             res = D.fit_pruned(X, tg, cfg)
         if res is None and ctx is not None and X.nnz > 0 and sel_in is None:
             # item-sharded fit: this rank solves the targets of its own Gram row blocks; the solver outputs (a few

@@ -259,8 +259,34 @@ def test_gram_adaptive_variant_equals_default():
             D.set_option("gram_adapt", mode)
             G1 = D.gram_full(dX).cpu().numpy()
             assert np.array_equal(G0, G1), mode
+        D.set_option("gram_adapt", 2)
+        # rank-sorted rows by the segmented sort (default: warp kernel for rows <= 64, CTA kernel above) vs the two global
+        # radix sorts of the first version: the same rows, so the same matrix bit for bit
+        D.set_option("gram_impl", 1)
+        assert np.array_equal(G0, D.gram_full(dX).cpu().numpy())
     finally:
         D.set_option("gram_adapt", 2)
+        D.set_option("gram_impl", 2)
+
+
+def test_gram_row_sort_all_row_lengths():
+    """Segmented row sort of the Gram preparation: rows of 1..64 entries (registers), 65..8192 (shared memory) and a row
+    beyond 8192 entries, which sends the matrix down the radix path.  Integer ratings: every Gram entry is an exact
+    integer sum, so the result must equal scipy's bit for bit whatever the summation order."""
+    from rtrec_b200 import device as D
+    rng = np.random.default_rng(5)
+    for longest in (3000, 9000):
+        U, I = 700, 10000
+        lens = np.concatenate([rng.integers(1, 65, 300), rng.integers(65, 700, 390), [1, 64, 65, 128, 129, 2048, 2049, longest, 0, 0]])
+        rows, cols = [], []
+        for u, n in enumerate(lens):
+            c = rng.choice(I, int(n), replace=False)
+            rows.append(np.full(len(c), u)); cols.append(c)
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        X = sp.csc_matrix((rng.integers(1, 6, len(rows)).astype(np.float32), (rows, cols)), shape=(U, I))
+        G = D.gram_full(D.DeviceMatrix.from_scipy(X)).cpu().numpy()
+        ref = np.asarray((X.T @ X).todense(), dtype=np.float32)
+        assert np.array_equal(G, ref), longest
 
 
 def test_predict_family_matches_scipy(golden):
@@ -360,7 +386,7 @@ def test_tensor_core_scoring_matches_exact_scores(rating):
         D.set_option("score_tc", 1)
 
 
-def test_pruned_all_features_fit_equals_dense_path():
+def test_pruned_fit_equals_dense_path():
     """rt_slim_fit_pruned: all-features fit from the Gram rows of the Cauchy-Schwarz candidates only.  Same W as the dense
     path (Gram entries are accumulated by a different kernel: agreement to float32 rounding, same non-zero pattern), same
     stats for the zero columns, far fewer Gram rows; falls back (None) when the candidates are most of the catalogue."""
@@ -396,8 +422,16 @@ def test_pruned_all_features_fit_equals_dense_path():
     dX2 = D.DeviceMatrix.from_scipy(sp.csc_matrix((r2.astype(np.float32), (u2, i2)), shape=(400, 300)))
     assert D.fit_pruned(dX2, torch.arange(300, dtype=torch.int32, device="cuda"), op._config(dX2)) is None
     assert D.last_pruned_rows > 300 // 4
-    # feature selection is not this path's business
-    assert D.fit_pruned(dX, tg, SLIMElastic({"nn_feature_selection": 20})._config(dX)) is None
+    # feature selection: a bulk fit takes the same path (columns without a live coordinate come back empty), a merge into
+    # an existing W does not (a returned zero deletes a stale entry)
+    opn = SLIMElastic({"nn_feature_selection": 20})
+    assert D.fit_pruned(dX, tg, opn._config(dX, into_empty_w=False)) is None
+    res_pn = D.fit_pruned(dX, tg, opn._config(dX))
+    assert res_pn is not None
+    Wpn = D.w_merge(None, I, res_pn).to_scipy_csc()
+    Wdn = D.w_merge(None, I, D.solve(G, I, tg, opn._config(dX, into_empty_w=False))).to_scipy_csc()
+    assert Wdn.nnz > 0 and np.array_equal(Wpn.indptr, Wdn.indptr) and np.array_equal(Wpn.indices, Wdn.indices)
+    assert np.abs(Wpn.data - Wdn.data).max() <= 1e-4 * np.abs(Wdn.data).max()
 
 
 @pytest.mark.parametrize("nn", [20, None])
