@@ -87,7 +87,8 @@ __global__ void pack_entries_kernel(const int *__restrict__ pidx, const float *_
 // 12-byte pairs) of the first version.  Rows of at most 64 entries are sorted by one warp in registers (two entries per
 // lane, bitonic network over shuffles), longer rows by one CTA in shared memory (bitonic, up to RS_BIG entries); ranks
 // within a row are distinct, so no stability question arises.  Rows longer than RS_BIG send the whole matrix down the
-// radix path (the launcher knows the longest row).
+// radix path (the launcher knows the longest row).  Three size classes: <= 64 (registers), <= 1,024 (a warp with its own
+// shared-memory slice), <= 8,192 (a CTA).
 constexpr int RS_BIG = 8192;
 constexpr int RS_NT = 256;
 
@@ -136,6 +137,60 @@ __global__ void __launch_bounds__(256) row_sort_small_kernel(int n_users, const 
     if (lane + 32 < n) { pidx[a + lane + 32] = k1; pval[a + lane + 32] = v1; }
 }
 
+// rows of 65 .. RS_MID entries: one WARP per row, bitonic network in the warp's own shared-memory slice -- eight rows in
+// flight per CTA and no CTA barrier anywhere (the CTA kernel below spent its time at barriers between 36+ stages)
+constexpr int RS_MID = 1024;
+constexpr int RS_MID_WARPS = 8;
+
+__global__ void __launch_bounds__(RS_MID_WARPS * 32) row_sort_mid_kernel(int n_users, const int *__restrict__ rptr,
+                                                                         const int *__restrict__ ridx, const float *__restrict__ rval,
+                                                                         const int *__restrict__ rank_of, int *__restrict__ pidx,
+                                                                         float *__restrict__ pval, int *__restrict__ next_row) {
+    extern __shared__ __align__(16) int rs_smem[];     // per warp: keys[RS_MID], values[RS_MID]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int *sk = rs_smem + warp * 2 * RS_MID;
+    float *sv = reinterpret_cast<float *>(sk + RS_MID);
+    for (;;) {
+        int u0 = 0;
+        if (lane == 0) u0 = atomicAdd(next_row, 32);
+        u0 = __shfl_sync(0xffffffffu, u0, 0);
+        if (u0 >= n_users) break;
+        // lengths of the 32 claimed rows, one per lane; the warp then walks those in its size class
+        const int my_a = u0 + lane < n_users ? rptr[u0 + lane] : 0;
+        const int my_n = u0 + lane < n_users ? rptr[u0 + lane + 1] - my_a : 0;
+        unsigned todo = __ballot_sync(0xffffffffu, my_n > 64 && my_n <= RS_MID);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int a = __shfl_sync(0xffffffffu, my_a, l), n = __shfl_sync(0xffffffffu, my_n, l);
+            int np = 128;
+            while (np < n) np <<= 1;
+            for (int e = lane; e < np; e += 32) {
+                if (e < n) { sk[e] = rank_of[ridx[a + e]]; sv[e] = rval[a + e]; }
+                else { sk[e] = 0x7fffffff; sv[e] = 0.f; }
+            }
+            __syncwarp();
+            for (int size = 2; size <= np; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int t = lane; t < (np >> 1); t += 32) {
+                        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                        const int hi = lo | stride;
+                        const bool up = (lo & size) == 0;
+                        const int ka = sk[lo], kb = sk[hi];
+                        if ((ka > kb) == up) {
+                            sk[lo] = kb; sk[hi] = ka;
+                            const float f = sv[lo]; sv[lo] = sv[hi]; sv[hi] = f;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int e = lane; e < n; e += 32) { pidx[a + e] = sk[e]; pval[a + e] = sv[e]; }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RS_NT) row_sort_big_kernel(int n_users, const int *__restrict__ rptr, const int *__restrict__ ridx,
                                                             const float *__restrict__ rval, const int *__restrict__ rank_of,
                                                             int *__restrict__ pidx, float *__restrict__ pval,
@@ -146,7 +201,7 @@ __global__ void __launch_bounds__(RS_NT) row_sort_big_kernel(int n_users, const 
     __shared__ int s_u;
     const int tid = threadIdx.x;
     for (;;) {
-        // rows are claimed 64 at a time; short rows (the warp kernel's) are skipped
+        // rows are claimed 64 at a time; rows of at most RS_MID entries (the warp kernels') are skipped
         __syncthreads();
         if (tid == 0) s_u = atomicAdd(next_row, 64);
         __syncthreads();
@@ -154,7 +209,7 @@ __global__ void __launch_bounds__(RS_NT) row_sort_big_kernel(int n_users, const 
         if (u0 >= n_users) break;
         for (int u = u0; u < min(u0 + 64, n_users); ++u) {
             const int a = rptr[u], n = rptr[u + 1] - a;
-            if (n <= 64) continue;                              // (uniform: every thread reads the same rptr)
+            if (n <= RS_MID) continue;                          // (uniform: every thread reads the same rptr)
             int np = 128;
             while (np < n) np <<= 1;
             __syncthreads();
@@ -704,6 +759,14 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
                                                                                             d_rank_of, P.pidx, P.pval);
         RT_CHECK_LAUNCH();
         if (max_len > 64) {
+            int *d_next_mid = (int *)P.counter + 5;
+            const size_t msmem = (size_t)RS_MID_WARPS * RS_MID * 8;
+            RT_CUDA(cudaFuncSetAttribute(row_sort_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+            row_sort_mid_kernel<<<rt::sm_count() * 3, RS_MID_WARPS * 32, msmem, st>>>(n_users, d_rptr, d_ridx, d_rval, d_rank_of, P.pidx,
+                                                                                     P.pval, d_next_mid);
+            RT_CHECK_LAUNCH();
+        }
+        if (max_len > RS_MID) {
             int *d_next = (int *)P.counter + 4;
             const size_t smem = (size_t)RS_BIG * 8;
             RT_CUDA(cudaFuncSetAttribute(row_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
