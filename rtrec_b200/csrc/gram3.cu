@@ -85,12 +85,12 @@ __global__ void pack_entries_kernel(const int *__restrict__ pidx, const float *_
 // The Gram kernel wants every user's row ordered by the popularity rank of its items.  The rows are already contiguous
 // (CSR), so this is a sort WITHIN each row -- not the two global radix sorts (rank bits, then user bits: five passes over
 // 12-byte pairs) of the first version.  Rows of at most 64 entries are sorted by one warp in registers (two entries per
-// lane, bitonic network over shuffles), longer rows by one CTA in shared memory (bitonic, up to RS_BIG entries); ranks
-// within a row are distinct, so no stability question arises.  Rows longer than RS_BIG send the whole matrix down the
-// radix path (the launcher knows the longest row).  Three size classes: <= 64 (registers), <= 1,024 (a warp with its own
-// shared-memory slice), <= 8,192 (a CTA).
-constexpr int RS_BIG = 8192;
-constexpr int RS_NT = 256;
+// lane, bitonic network over shuffles).  Longer rows are sorted by COUNTING: the ranks of one row are distinct numbers
+// below n_items, so a team (a one-warp CTA for catalogues up to 64k items, a wider CTA above) marks them in a shared-memory
+// bitmap of n_items bits, prefix-sums the population counts of the bitmap words, and every entry then reads its position:
+// O(row + n_items / 32) per row, no compare-exchange network, any row length, and the host never needs the longest row
+// (no device->host sync in front of the Gram kernel).  Catalogues whose bitmap does not fit one CTA's shared memory
+// (> ~900k items) keep the radix path.
 
 __device__ __forceinline__ void rs_cx(int &ka, float &va, int &kb, float &vb, bool up) {   // compare-exchange two entries
     if ((ka > kb) == up) { const int t = ka; ka = kb; kb = t; const float f = va; va = vb; vb = f; }
@@ -137,113 +137,60 @@ __global__ void __launch_bounds__(256) row_sort_small_kernel(int n_users, const 
     if (lane + 32 < n) { pidx[a + lane + 32] = k1; pval[a + lane + 32] = v1; }
 }
 
-// rows of 65 .. RS_MID entries: one WARP per row, bitonic network in the warp's own shared-memory slice -- eight rows in
-// flight per CTA and no CTA barrier anywhere (the CTA kernel below spent its time at barriers between 36+ stages)
-constexpr int RS_MID = 1024;
-constexpr int RS_MID_WARPS = 8;
-
-__global__ void __launch_bounds__(RS_MID_WARPS * 32) row_sort_mid_kernel(int n_users, const int *__restrict__ rptr,
-                                                                         const int *__restrict__ ridx, const float *__restrict__ rval,
-                                                                         const int *__restrict__ rank_of, int *__restrict__ pidx,
-                                                                         float *__restrict__ pval, int *__restrict__ next_row) {
-    extern __shared__ __align__(16) int rs_smem[];     // per warp: keys[RS_MID], values[RS_MID]
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int *sk = rs_smem + warp * 2 * RS_MID;
-    float *sv = reinterpret_cast<float *>(sk + RS_MID);
+// rows of more than 64 entries: counting sort over a bitmap of ranks, one row per CTA at a time (blockDim.x = 32 .. 256)
+__global__ void __launch_bounds__(256) row_sort_bitmap_kernel(int n_users, int n_items, const int *__restrict__ rptr,
+                                                              const int *__restrict__ ridx, const float *__restrict__ rval,
+                                                              const int *__restrict__ rank_of, int *__restrict__ pidx,
+                                                              float *__restrict__ pval, int *__restrict__ next_row) {
+    extern __shared__ __align__(16) unsigned rs_smem[];      // bits[nwords], then pre[nwords]
+    __shared__ int s_claim, s_warp_tot[8];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int nwords = (n_items + 31) >> 5;
+    unsigned *bits = rs_smem;
+    int *pre = reinterpret_cast<int *>(rs_smem + nwords);
+    const int seg = ((nwords + nt - 1) / nt) | 1;            // words per thread in the prefix pass (odd: no bank conflicts)
     for (;;) {
-        int u0 = 0;
-        if (lane == 0) u0 = atomicAdd(next_row, 32);
-        u0 = __shfl_sync(0xffffffffu, u0, 0);
-        if (u0 >= n_users) break;
-        // lengths of the 32 claimed rows, one per lane; the warp then walks those in its size class
-        const int my_a = u0 + lane < n_users ? rptr[u0 + lane] : 0;
-        const int my_n = u0 + lane < n_users ? rptr[u0 + lane + 1] - my_a : 0;
-        unsigned todo = __ballot_sync(0xffffffffu, my_n > 64 && my_n <= RS_MID);
-        while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int a = __shfl_sync(0xffffffffu, my_a, l), n = __shfl_sync(0xffffffffu, my_n, l);
-            int np = 128;
-            while (np < n) np <<= 1;
-            for (int e = lane; e < np; e += 32) {
-                if (e < n) { sk[e] = rank_of[ridx[a + e]]; sv[e] = rval[a + e]; }
-                else { sk[e] = 0x7fffffff; sv[e] = 0.f; }
-            }
-            __syncwarp();
-            for (int size = 2; size <= np; size <<= 1) {
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                    for (int t = lane; t < (np >> 1); t += 32) {
-                        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                        const int hi = lo | stride;
-                        const bool up = (lo & size) == 0;
-                        const int ka = sk[lo], kb = sk[hi];
-                        if ((ka > kb) == up) {
-                            sk[lo] = kb; sk[hi] = ka;
-                            const float f = sv[lo]; sv[lo] = sv[hi]; sv[hi] = f;
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            for (int e = lane; e < n; e += 32) { pidx[a + e] = sk[e]; pval[a + e] = sv[e]; }
-            __syncwarp();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(RS_NT) row_sort_big_kernel(int n_users, const int *__restrict__ rptr, const int *__restrict__ ridx,
-                                                            const float *__restrict__ rval, const int *__restrict__ rank_of,
-                                                            int *__restrict__ pidx, float *__restrict__ pval,
-                                                            int *__restrict__ next_row) {
-    extern __shared__ __align__(16) int rs_smem[];     // keys[RS_BIG], then values[RS_BIG]
-    int *sk = rs_smem;
-    float *sv = reinterpret_cast<float *>(rs_smem + RS_BIG);
-    __shared__ int s_u;
-    const int tid = threadIdx.x;
-    for (;;) {
-        // rows are claimed 64 at a time; rows of at most RS_MID entries (the warp kernels') are skipped
         __syncthreads();
-        if (tid == 0) s_u = atomicAdd(next_row, 64);
+        if (tid == 0) s_claim = atomicAdd(next_row, 32);
         __syncthreads();
-        const int u0 = s_u;
+        const int u0 = s_claim;
         if (u0 >= n_users) break;
-        for (int u = u0; u < min(u0 + 64, n_users); ++u) {
-            const int a = rptr[u], n = rptr[u + 1] - a;
-            if (n <= RS_MID) continue;                          // (uniform: every thread reads the same rptr)
-            int np = 128;
-            while (np < n) np <<= 1;
+        const int u1 = min(u0 + 32, n_users);
+        for (int u = u0; u < u1; ++u) {
+            const int a = rptr[u], n = rptr[u + 1] - a;       // (uniform: every thread reads the same rptr)
+            if (n <= 64) continue;
+            for (int w = tid; w < nwords; w += nt) bits[w] = 0u;
             __syncthreads();
-            for (int e = tid; e < np; e += RS_NT) {
-                if (e < n) { sk[e] = rank_of[ridx[a + e]]; sv[e] = rval[a + e]; }
-                else { sk[e] = 0x7fffffff; sv[e] = 0.f; }
+            for (int e = tid; e < n; e += nt) {
+                const int k = rank_of[ridx[a + e]];
+                atomicOr(&bits[k >> 5], 1u << (k & 31));
             }
             __syncthreads();
-            for (int size = 2; size <= np; size <<= 1) {
-                for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                    for (int t = tid; t < (np >> 1); t += RS_NT) {
-                        const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                        const int hi = lo | stride;
-                        const bool up = (lo & size) == 0;
-                        const int ka = sk[lo], kb = sk[hi];
-                        if ((ka > kb) == up) {
-                            sk[lo] = kb; sk[hi] = ka;
-                            const float f = sv[lo]; sv[lo] = sv[hi]; sv[hi] = f;
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-            for (int e = tid; e < n; e += RS_NT) { pidx[a + e] = sk[e]; pval[a + e] = sv[e]; }
-        }
-    }
-}
-
-__global__ void max_row_len_kernel(int n_users, const int *__restrict__ rptr, int *__restrict__ out) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    int v = u < n_users ? rptr[u + 1] - rptr[u] : 0;
+            // exclusive prefix of the word populations: per-thread segment totals, scanned over the CTA
+            const int w0 = min(tid * seg, nwords), w1 = min(w0 + seg, nwords);
+            int c = 0;
+            for (int w = w0; w < w1; ++w) c += __popc(bits[w]);
+            int incl = c;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_warp_tot[warp] = incl;
+            __syncthreads();
+            int run = incl - c;
+            for (int x = 0; x < warp; ++x) run += s_warp_tot[x];
+            for (int w = w0; w < w1; ++w) { pre[w] = run; run += __popc(bits[w]); }
+            __syncthreads();
+            for (int e = tid; e < n; e += nt) {
+                const int k = rank_of[ridx[a + e]];
+                const int pos = pre[k >> 5] + __popc(bits[k >> 5] & ((1u << (k & 31)) - 1u));
+                pidx[a + pos] = k;
+                pval[a + pos] = rval[a + e];
+            }
+            __syncthreads();
+        }
+    }
 }
 
 // one thread per stored entry e = (u, j): position of rank(j) inside the rank-sorted row of u; optionally
@@ -744,36 +691,23 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
     if (nnz == 0) { RT_CUDA(cudaStreamSynchronize(st)); return RT_OK; }
     RT_ARG(d_cidx && d_cval && d_ridx && d_rval, "null pointer");
     // ---- rank-sorted CSR ---------------------------------------------------------------------------
-    int max_len = 0;
-    {
-        int *d_max = (int *)P.counter + 2;      // (counter[0] is the task cursor of the lower-triangle kernel)
-        RT_CUDA(cudaMemsetAsync(P.counter, 0, 4 * sizeof(unsigned long long), st));
-        max_row_len_kernel<<<(n_users + bs - 1) / bs, bs, 0, st>>>(n_users, d_rptr, d_max);
-        RT_CHECK_LAUNCH();
-        RT_CUDA(cudaMemcpyAsync(&max_len, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
-        RT_CUDA(cudaStreamSynchronize(st));
-    }
-    if (max_len <= RS_BIG && rt::option(rt::OPT_GRAM_IMPL) != 1) {
-        // segmented sort: every row by the rank of its items (warp kernel for rows <= 64, CTA kernel for the rest)
+    const int nwords = (I + 31) >> 5;
+    const size_t bm_smem = (size_t)nwords * 8;
+    RT_CUDA(cudaMemsetAsync(P.counter, 0, 4 * sizeof(unsigned long long), st));   // ([0]: task cursor of the lower-triangle kernel)
+    if (bm_smem <= (size_t)rt::smem_optin() - 1024 && rt::option(rt::OPT_GRAM_IMPL) != 1) {
+        // segmented sort: every row by the rank of its items (registers for rows <= 64, bitmap counting sort for the rest)
         row_sort_small_kernel<<<(unsigned)(((int64_t)n_users * 32 + bs - 1) / bs), bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rval,
                                                                                             d_rank_of, P.pidx, P.pval);
         RT_CHECK_LAUNCH();
-        if (max_len > 64) {
-            int *d_next_mid = (int *)P.counter + 5;
-            const size_t msmem = (size_t)RS_MID_WARPS * RS_MID * 8;
-            RT_CUDA(cudaFuncSetAttribute(row_sort_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-            row_sort_mid_kernel<<<rt::sm_count() * 3, RS_MID_WARPS * 32, msmem, st>>>(n_users, d_rptr, d_ridx, d_rval, d_rank_of, P.pidx,
-                                                                                     P.pval, d_next_mid);
-            RT_CHECK_LAUNCH();
-        }
-        if (max_len > RS_MID) {
-            int *d_next = (int *)P.counter + 4;
-            const size_t smem = (size_t)RS_BIG * 8;
-            RT_CUDA(cudaFuncSetAttribute(row_sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            row_sort_big_kernel<<<rt::sm_count() * 3, RS_NT, smem, st>>>(n_users, d_rptr, d_ridx, d_rval, d_rank_of, P.pidx, P.pval,
-                                                                       d_next);
-            RT_CHECK_LAUNCH();
-        }
+        int *d_next = (int *)P.counter + 4;
+        const int team = nwords <= 2048 ? 32 : nwords <= 16384 ? 128 : 256;
+        RT_CUDA(cudaFuncSetAttribute(row_sort_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        int per_sm = 1;
+        RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, row_sort_bitmap_kernel, team, bm_smem));
+        if (per_sm < 1) per_sm = 1;
+        row_sort_bitmap_kernel<<<rt::sm_count() * per_sm, team, bm_smem, st>>>(n_users, I, d_rptr, d_ridx, d_rval, d_rank_of, P.pidx,
+                                                                             P.pval, d_next);
+        RT_CHECK_LAUNCH();
     } else {
         const unsigned grid = (unsigned)(((int64_t)n_users * 32 + bs - 1) / bs);
         relabel_keys_kernel<<<grid, bs, 0, st>>>(n_users, d_rptr, d_ridx, d_rank_of, P.keys);

@@ -91,8 +91,9 @@ class DeviceMatrix:
         import scipy.sparse as sp
         t = require_cuda()
         csr = sp.csr_matrix(X, dtype=np.float32)
+        csr.sum_duplicates()        # (the kernels rely on one stored entry per (user, item), as the device store guarantees)
         csr.sort_indices()
-        csc = sp.csc_matrix(X, dtype=np.float32)
+        csc = sp.csc_matrix(csr)
         csc.sort_indices()
         n_users, n_items = csr.shape
         ccol = np.repeat(np.arange(n_items, dtype=np.int32), np.diff(csc.indptr).astype(np.int64))

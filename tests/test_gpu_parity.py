@@ -270,13 +270,14 @@ def test_gram_adaptive_variant_equals_default():
 
 
 def test_gram_row_sort_all_row_lengths():
-    """Segmented row sort of the Gram preparation: rows of 1..64 entries (registers), 65..8192 (shared memory) and a row
-    beyond 8192 entries, which sends the matrix down the radix path.  Integer ratings: every Gram entry is an exact
-    integer sum, so the result must equal scipy's bit for bit whatever the summation order."""
+    """Segmented row sort of the Gram preparation: rows of 1..64 entries (registers) and longer rows (counting sort over a
+    shared-memory bitmap of ranks: one-warp CTAs up to 64k items, multi-warp CTAs above), against the radix path.  Integer
+    ratings: every Gram entry is an exact integer sum, so the result must equal scipy's bit for bit whatever the summation
+    order."""
     from rtrec_b200 import device as D
     rng = np.random.default_rng(5)
-    for longest in (3000, 9000):
-        U, I = 700, 10000
+    for I, longest in ((10000, 3000), (10000, 9000), (70000, 20000)):
+        U = 700
         lens = np.concatenate([rng.integers(1, 65, 300), rng.integers(65, 700, 390), [1, 64, 65, 128, 129, 2048, 2049, longest, 0, 0]])
         rows, cols = [], []
         for u, n in enumerate(lens):
@@ -284,9 +285,18 @@ def test_gram_row_sort_all_row_lengths():
             rows.append(np.full(len(c), u)); cols.append(c)
         rows, cols = np.concatenate(rows), np.concatenate(cols)
         X = sp.csc_matrix((rng.integers(1, 6, len(rows)).astype(np.float32), (rows, cols)), shape=(U, I))
-        G = D.gram_full(D.DeviceMatrix.from_scipy(X)).cpu().numpy()
-        ref = np.asarray((X.T @ X).todense(), dtype=np.float32)
-        assert np.array_equal(G, ref), longest
+        dX = D.DeviceMatrix.from_scipy(X)
+        sel = np.unique(np.concatenate([rng.integers(0, I, 400), cols[-longest:][:50], [0, I - 1]]))
+        ref = np.asarray((X[:, sel].T @ X).todense(), dtype=np.float32)
+        for impl in (0, 1):
+            D.set_option("gram_impl", impl)
+            try:
+                G = D.gram_full(dX)
+                got = G[D.to_dev(sel, np.int64)][:, :I].cpu().numpy()
+                del G
+            finally:
+                D.set_option("gram_impl", 0)
+            assert np.array_equal(got, ref), (I, longest, impl)
 
 
 def test_predict_family_matches_scipy(golden):
