@@ -390,6 +390,9 @@ int rt_slim_recommend(const int32_t *d_rptr, const int32_t *d_ridx, const float 
  *                   score tile, float bits) int32 pairs; padding slots carry value 0 and point at a
  *                   dummy float behind the tile; 8-byte aligned.
  * rt_slim_recommend_packed is rt_slim_recommend with the pack; results are identical bit for bit.
+ * In rt_slim_recommend_packed only, d_users[q] < 0 marks an unused query slot: its answer is empty (count 0, ids -1).
+ * Callers that re-score a device-computed list of users in a fixed number of slots (the hand-backs of
+ * rt_slim_recommend_tc) use this to avoid a device->host read of the list length.
  */
 int rt_score_tile(int32_t n_items, int32_t j_begin, int32_t j_end, int32_t *h_tile, int32_t *h_n_tiles);
 int rt_w_pack_plan(const int32_t *d_wrptr, const int32_t *d_wridx, int32_t n_items, int32_t j_begin,

@@ -202,9 +202,19 @@ __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict
     const bool valid = e < nnz;
     int jp = -1;
     unsigned long long work = 0;
+    // columns of the CTA's first and last entry (two full searches per CTA); every thread then searches between them only
+    __shared__ int s_col[2];
+    if (threadIdx.x < 2) {
+        const int64_t e0 = (int64_t)blockIdx.x * blockDim.x;
+        const int ee = (int)(threadIdx.x == 0 ? e0 : min(e0 + (int64_t)blockDim.x, nnz) - 1);
+        int lo = 0, hi = n_items;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cptr[mid] <= ee) lo = mid; else hi = mid; }
+        s_col[threadIdx.x] = lo;
+    }
+    __syncthreads();
     if (valid) {
         // column of entry e: last j with cptr[j] <= e
-        int lo = 0, hi = n_items;
+        int lo = s_col[0], hi = s_col[1] + 1;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (cptr[mid] <= (int)e) lo = mid; else hi = mid; }
         jp = rank_of[lo];
         // block-cyclic mode: positions are only needed for the columns this part owns (cost == nullptr there)
@@ -387,19 +397,29 @@ gram_lower_kernel(int row_begin, int row_end, const int *__restrict__ chunk_star
     }
 }
 
-// upper triangle <- transpose of the lower triangle (32 x 32 tiles through shared memory)
+// upper triangle <- transpose of the lower triangle: 64 x 64 tiles through shared memory, one CTA per tile of the
+// triangle (linear tile index -> (by, bx), no empty CTAs), sixteen loads in flight per thread before the barrier
 __global__ void __launch_bounds__(256) gram_mirror_kernel(float *__restrict__ G, int n, int64_t ld) {
-    __shared__ float tile[32][33];
-    const int bx = blockIdx.x, by = blockIdx.y;
-    if (bx > by) return;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int row = by * 32 + r, col = bx * 32 + tx;
-        tile[r][tx] = (row < n && col < n) ? G[(size_t)row * ld + col] : 0.0f;
+    __shared__ float tile[64][65];
+    const unsigned t = blockIdx.x;
+    int by = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while ((unsigned)(by + 1) * (unsigned)(by + 2) / 2u <= t) ++by;
+    while ((unsigned)by * (unsigned)(by + 1) / 2u > t) --by;
+    const int bx = (int)(t - (unsigned)by * (unsigned)(by + 1) / 2u);      // bx <= by
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int row = by * 64 + ty + 4 * i, col = bx * 64 + tx;
+        v[i] = (row < n && col < n) ? G[(size_t)row * ld + col] : 0.0f;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[ty + 4 * i][tx] = v[i];
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int row = bx * 32 + r, col = by * 32 + tx;  // destination (upper)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int r = ty + 4 * i;
+        const int row = bx * 64 + r, col = by * 64 + tx;  // destination (upper)
         if (row < n && col < n && col > row) G[(size_t)row * ld + col] = tile[tx][r];
     }
 }
@@ -922,8 +942,8 @@ extern "C" int rt_gram_finish(int32_t n_items, float *d_Gp, int64_t ldgp, const 
     RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items, "arguments");
     RT_ARG(d_Gp != d_G, "rt_gram_finish is not in-place");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = (n_items + 31) / 32;
-    gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
+    const unsigned nt = (unsigned)((n_items + 63) / 64);
+    gram_mirror_kernel<<<nt * (nt + 1) / 2, 256, 0, st>>>(d_Gp, n_items, ldgp);
     RT_CHECK_LAUNCH();
     return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st);
 }
@@ -934,8 +954,8 @@ extern "C" int rt_gram_finish_rowmax(int32_t n_items, float *d_Gp, int64_t ldgp,
     RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items && d_rowmax && h_has_rowmax, "arguments");
     RT_ARG(d_Gp != d_G, "rt_gram_finish is not in-place");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nt = (n_items + 31) / 32;
-    gram_mirror_kernel<<<dim3(nt, nt), 256, 0, st>>>(d_Gp, n_items, ldgp);
+    const unsigned nt = (unsigned)((n_items + 63) / 64);
+    gram_mirror_kernel<<<nt * (nt + 1) / 2, 256, 0, st>>>(d_Gp, n_items, ldgp);
     RT_CHECK_LAUNCH();
     return launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st, d_rowmax, h_has_rowmax);
 }

@@ -169,6 +169,11 @@ recommend3_kernel(const int *__restrict__ rptr, const int *__restrict__ ridx, co
         // cheap users and no CTA is left alone with an expensive one
         const int q = order ? order[sh.q] : sh.q;
         const int u = users[q];
+        if (u < 0) {   // an unused query slot (see query_work_kernel): empty answer
+            for (int e = tid; e < k; e += S3_NT) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
+            if (tid == 0) out_cnt[q] = 0;
+            continue;
+        }
         const int r0 = rptr[u], r1 = rptr[u + 1];
         int nbest = 0;
         int tau = 0;
@@ -353,7 +358,10 @@ __global__ void __launch_bounds__(256) query_work_kernel(const int *__restrict__
     const int u = users[q];
     const bool whole = j_begin == 0 && j_end == n_items;
     unsigned long long work = 0;
-    for (int p = rptr[u] + lane; p < rptr[u + 1]; p += 32) {
+    // a negative user id marks an unused query slot (fixed-size re-scoring batches of the tensor-core path, whose real
+    // length only the device knows): answered here with an empty list, in both modes
+    const int p_end = u < 0 ? 0 : rptr[u + 1];
+    for (int p = (u < 0 ? 0 : rptr[u]) + lane; p < p_end; p += 32) {
         const int i = ridx[p];
         int a = wrptr[i], b = wrptr[i + 1];
         if (!whole && b > a) { a = lower_bound3(wridx, a, b, j_begin); b = lower_bound3(wridx, a, b, j_end); }
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(256) query_work_kernel(const int *__restrict__
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) work += __shfl_xor_sync(0xffffffffu, work, o);
-    const bool skip = sparse && work == 0;
+    const bool skip = (sparse && work == 0) || u < 0;
     if (skip) {
         for (int e = lane; e < k; e += 32) { out_ids[(size_t)q * k + e] = -1; out_scores[(size_t)q * k + e] = 0.0f; }
     }

@@ -565,11 +565,20 @@ def values_bf16_exact(X: DeviceMatrix) -> Tuple[bool, bool]:
     return hit
 
 
-def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int, debug_scores: bool = False):
+TC_REDO_MIN_SLOTS, TC_REDO_DIV = 256, 16   # no_sync scoring: max(256, Q // 16) slots for users handed back by the tensor-core path
+
+
+def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int, debug_scores: bool = False,
+                 no_sync: bool = False):
     """Scoring with the heavy rows of W on the tensor cores (score_tc.cu); scores agree with the exact kernels to ~1e-6
     relative.  Returns device (ids, scores, cnt) like ``recommend``, or None when the preconditions do not hold.  Users the
     fast path cannot finish (light-row table overflow, dense-mode lists with fewer than k positive scores) are re-scored
-    by the exact kernel."""
+    by the exact kernel.
+
+    ``no_sync``: the host does not wait for the list of those users.  A fixed number of slots (``Q // 16``, at least 256)
+    is re-scored -- the flagged users first, the spare slots into a scratch row -- and a fourth result, the device count
+    of flagged users, tells the caller afterwards whether the slots were enough (``> slots``: call again without
+    ``no_sync``).  Lets a caller queue many batches back to back (``SLIMElastic.recommend_lists``)."""
     t = require_cuda()
     Q = int(users.numel())
     if k > TC_KMAX or Q == 0:
@@ -580,7 +589,7 @@ def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: 
     x_nonneg, x_exact = values_bf16_exact(X)
     if not x_nonneg:
         return None
-    ids = empty(Q * k, t.int32); scores = empty(Q * k, t.float32); cnt = empty(Q, t.int32)
+    ids = empty((Q + 1) * k, t.int32); scores = empty((Q + 1) * k, t.float32); cnt = empty(Q + 1, t.int32)   # (+1: scratch row)
     tc_ids = empty(Q * 32, t.int32); tc_sc = empty(Q * 32, t.float32); tc_cnt = empty(Q, t.int32)
     fb = empty(Q, t.int32)
     i_pad = (W.n_items + 127) // 128 * 128
@@ -590,32 +599,49 @@ def recommend_tc(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: 
                                            1 if filter_interacted else 0, int(mode), 1 if x_exact else 3, ptr(tc_ids), ptr(tc_sc),
                                            ptr(tc_cnt), ptr(ids), ptr(scores), ptr(cnt), ptr(fb), ptr(dbg), stream_ptr()),
           "rt_slim_recommend_tc")
-    ids, scores = ids.view(Q, k), scores.view(Q, k)
+    ids, scores = ids.view(Q + 1, k), scores.view(Q + 1, k)
+    global _score_tc
+    if no_sync and not debug_scores:
+        slots = min(Q, max(TC_REDO_MIN_SLOTS, Q // TC_REDO_DIV))
+        flag = (fb != 0).to(t.int32)
+        hit, redo = t.topk(flag, slots)
+        redo = t.where(hit != 0, redo, Q)                       # spare slots: user id -1 (no query), result to the scratch row
+        keep, _score_tc = _score_tc, 0
+        try:
+            r_ids, r_sc, r_cnt = recommend(X, t.nn.functional.pad(users, (0, 1), value=-1)[redo].contiguous(), W, k,
+                                           filter_interacted, mode)
+        finally:
+            _score_tc = keep
+        ids[redo] = r_ids; scores[redo] = r_sc; cnt[redo] = r_cnt
+        return ids[:Q], scores[:Q], cnt[:Q], (flag.sum(dtype=t.int32), slots)
     redo = t.nonzero(fb).flatten()
     if int(redo.numel()):
-        global _score_tc
         keep, _score_tc = _score_tc, 0
         try:
             r_ids, r_sc, r_cnt = recommend(X, users[redo].contiguous(), W, k, filter_interacted, mode)
         finally:
             _score_tc = keep
         ids[redo] = r_ids; scores[redo] = r_sc; cnt[redo] = r_cnt
+    ids, scores, cnt = ids[:Q], scores[:Q], cnt[:Q]
     if debug_scores:
         return ids, scores, cnt, dbg, (tc_ids.view(Q, 32), tc_sc.view(Q, 32), tc_cnt), redo
     return ids, scores, cnt
 
 
 def recommend(X: DeviceMatrix, users, W: DeviceW, k: int, filter_interacted: bool, mode: int,
-              j_begin: int = 0, j_end: Optional[int] = None):
+              j_begin: int = 0, j_end: Optional[int] = None, no_sync: bool = False):
     """Fused scoring + filter + top-k for a batch of users (K6).  Returns device (ids, scores, cnt).  Large batches over the
-    whole item range go to the tensor-core path when W and X qualify (``recommend_tc``), everything else to the exact kernels."""
+    whole item range go to the tensor-core path when W and X qualify (``recommend_tc``), everything else to the exact kernels.
+    ``no_sync``: see ``recommend_tc``; a fourth result (None, or (device count, slots)) is returned."""
     t = require_cuda()
     Q = int(users.numel())
     if (_score_tc and _score_impl == 3 and Q >= TC_MIN_QUERIES and k <= TC_KMAX and j_begin == 0
             and (j_end is None or j_end == W.n_items)):
-        out = recommend_tc(X, users, W, k, filter_interacted, mode)
+        out = recommend_tc(X, users, W, k, filter_interacted, mode, no_sync=no_sync)
         if out is not None:
             return out
+    if no_sync:
+        return recommend(X, users, W, k, filter_interacted, mode, j_begin, j_end) + (None,)
     ids = empty(max(Q * k, 1), t.int32)
     scores = empty(max(Q * k, 1), t.float32)
     cnt = empty(max(Q, 1), t.int32)

@@ -391,6 +391,56 @@ def test_tensor_core_scoring_matches_exact_scores(rating):
         # the public entry point takes this path for large batches by itself
         a = D.recommend(dX, users, dW, 10, True, RT_TOPK_SPARSE)
         assert a[0].shape == (n_users, 10)
+        # queued form (no host wait for the hand-back list): same lists; too few slots are reported, and the list
+        # builder then repeats the chunk the waiting way
+        from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+        def same_lists(x, y):
+            # (two runs of the tensor-core path agree up to the order of a few float atomics in the light-row table)
+            assert len(x) == len(y)
+            return sum(int(p == q) for p, q in zip(x, y)) >= 0.995 * len(x)
+
+        def as_lists(r):
+            return [row[:c].tolist() for row, c in zip(r[0].cpu().numpy(), r[2].cpu().numpy())]
+
+        for mode in (RT_TOPK_SPARSE, RT_TOPK_DENSE):
+            a = D.recommend(dX, users, dW, 10, True, mode)
+            b = D.recommend(dX, users, dW, 10, True, mode, no_sync=True)
+            n_back, slots = int(b[3][0]), b[3][1]
+            if n_back > slots:      # more hand-backs than slots: the caller is told, and has to ask again the waiting way
+                old_slots, D.TC_REDO_MIN_SLOTS = D.TC_REDO_MIN_SLOTS, n_back
+                b = D.recommend(dX, users, dW, 10, True, mode, no_sync=True)
+                D.TC_REDO_MIN_SLOTS = old_slots
+                assert int(b[3][0]) == n_back and b[3][1] == n_back
+            assert torch.equal(a[2], b[2]) and same_lists(as_lists(a), as_lists(b))
+            valid = (torch.arange(10, device="cuda")[None, :] < a[2][:, None]).cpu().numpy()
+            assert np.abs(a[1].cpu().numpy() - b[1].cpu().numpy())[valid].max() <= 1e-5 * float(a[1].cpu().numpy()[valid].max())
+            op = SLIMElastic({})
+            op._W = dW
+            want = as_lists(a)
+            assert same_lists(op.recommend_lists(uh, dX, 10, True, dense_output=mode == RT_TOPK_DENSE), want)
+            if n_back > 1:
+                old_slots, old_div, old_chunk = D.TC_REDO_MIN_SLOTS, D.TC_REDO_DIV, SLIMElastic._LIST_CHUNK
+                D.TC_REDO_MIN_SLOTS, D.TC_REDO_DIV, SLIMElastic._LIST_CHUNK = 1, 1 << 30, 1 << 30
+                try:
+                    short = D.recommend(dX, users, dW, 10, True, mode, no_sync=True)[3]
+                    assert int(short[0]) == n_back and short[1] == 1
+                    assert same_lists(op.recommend_lists(uh, dX, 10, True, dense_output=mode == RT_TOPK_DENSE), want)
+                finally:
+                    D.TC_REDO_MIN_SLOTS, D.TC_REDO_DIV, SLIMElastic._LIST_CHUNK = old_slots, old_div, old_chunk
+        # unused query slots (user id -1) of the exact kernels: empty answers, the other rows untouched
+        D.set_option("score_tc", 0)
+        try:
+            for mode in (RT_TOPK_SPARSE, RT_TOPK_DENSE):
+                for nq in (200, n_users):            # without / with the work-ordered queue
+                    uu = users[:nq].clone()
+                    uu[::3] = -1
+                    r = D.recommend(dX, uu, dW, 10, True, mode)
+                    f = D.recommend(dX, users[:nq], dW, 10, True, mode)
+                    hole = (uu < 0)
+                    assert int(r[2][hole].abs().sum()) == 0 and bool((r[0][hole] == -1).all())
+                    assert torch.equal(r[0][~hole], f[0][~hole]) and torch.equal(r[1][~hole], f[1][~hole]) and torch.equal(r[2][~hole], f[2][~hole])
+        finally:
+            D.set_option("score_tc", 1)
     finally:
         D.PACK_MIN_ROW = old_min
         D.set_option("score_tc", 1)
