@@ -487,11 +487,15 @@ int rt_eval_metrics(const int32_t *d_ids, const int32_t *d_cnt, int32_t n_query,
  * 2 = staged/pipelined kernel, default 2; the packed third generation has its own entry point);
  * "gram_impl", "gram_slice", "gram_ranges", "gram_adapt" (variants of gram_lower_kernel: 0 = four unconditional
  * batches per rater, 1 = segment-length guards, 2 = guards + packed (relative index, value) entries, the default) for
- * the Gram kernels;
+ * the Gram kernels; "gram_head" (1 = the 2,048 most popular items' corner of rt_gram_lower goes to the tensor cores when the
+ * values are exact in bf16, the sums exact in fp32 and the corner is dense enough -- gram_tc.cu --, 0 = never; default 1);
  * "solve_impl" for rt_slim_solve (1 = one CTA per target column for every configuration, 2 = one warp
  * per target column when nn <= 64, default 2; 3 = like 2 but every 7th target is handed to the CTA
  * kernel, a test hook for the overflow fallback).  Returns RT_ERR_ARG for an unknown name. */
 int rt_set_option(const char *name, int32_t value);
+
+/* Rows of the Gram matrix the last rt_gram_lower call of this process computed on the tensor cores (0 or 2048). */
+int32_t rt_gram_last_head(void);
 
 /* Frees the library-owned device scratch (grow-only arenas reused across calls). */
 void rt_release_scratch(void);

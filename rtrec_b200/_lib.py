@@ -105,6 +105,7 @@ PROTOTYPES = {
     "rt_lru_replay": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, C.POINTER(_I64)]),
     "rt_eval_metrics": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _P]),
     "rt_set_option": (C.c_int, [C.c_char_p, _I32]),
+    "rt_gram_last_head": (_I32, []),
     "rt_release_scratch": (None, []),
     "rt_launch_count": (_I64, []),
     "rt_launch_count_reset": (None, []),

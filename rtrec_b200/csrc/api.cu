@@ -66,7 +66,7 @@ void *scratch(int slot, size_t bytes) {
     return p;
 }
 
-static int g_opts[OPT_COUNT] = {2, 2, 2, 0, 0, 2};
+static int g_opts[OPT_COUNT] = {2, 2, 2, 0, 0, 2, 1};
 int option(int key) { return (key >= 0 && key < OPT_COUNT) ? g_opts[key] : 0; }
 
 int sm_count() { return query_device() == RT_OK ? g_sm_count : 148; }
@@ -92,6 +92,7 @@ extern "C" int rt_set_option(const char *name, int32_t value) {
     if (!strcmp(name, "gram_slice")) { rt::g_opts[rt::OPT_GRAM_SLICE] = value; return RT_OK; }
     if (!strcmp(name, "gram_ranges")) { rt::g_opts[rt::OPT_GRAM_RANGES] = value; return RT_OK; }
     if (!strcmp(name, "gram_adapt")) { rt::g_opts[rt::OPT_GRAM_ADAPT] = value; return RT_OK; }
+    if (!strcmp(name, "gram_head")) { rt::g_opts[rt::OPT_GRAM_HEAD] = value; return RT_OK; }
     if (!strcmp(name, "solve_impl")) { rt::g_opts[rt::OPT_SOLVE_IMPL] = value; return RT_OK; }
     rt::set_error("rt_set_option: unknown option '%s'", name);
     return RT_ERR_ARG;

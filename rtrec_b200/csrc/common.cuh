@@ -13,12 +13,12 @@ void count_launch(int n = 1);
 int sm_count();
 int smem_optin();
 // tuning switches settable through rt_set_option(): which kernel generation serves an entry point
-enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_SOLVE_IMPL, OPT_GRAM_SLICE, OPT_GRAM_RANGES, OPT_GRAM_ADAPT, OPT_COUNT };
+enum { OPT_SCORE_IMPL = 0, OPT_GRAM_IMPL, OPT_SOLVE_IMPL, OPT_GRAM_SLICE, OPT_GRAM_RANGES, OPT_GRAM_ADAPT, OPT_GRAM_HEAD, OPT_COUNT };
 int option(int key);
 // Grow-only device scratch owned by the library (one buffer per slot).  Reused across calls: the
 // library assumes one caller thread and stream-ordered use (see include/rtrec_b200.h).
 void *scratch(int slot, size_t bytes);
-enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_GRAM_PACK, SCR_GRAM_SEL, SCR_SLOTS };
+enum { SCR_SOLVE = 0, SCR_WMAT_A, SCR_WMAT_B, SCR_CUB, SCR_STORE_A, SCR_STORE_B, SCR_MISC, SCR_SCORE, SCR_SOLVE_FLAGS, SCR_GRAM_PACK, SCR_GRAM_SEL, SCR_GRAM_HEAD, SCR_SLOTS };
 
 #define RT_CUDA(expr)                                                                              \
     do {                                                                                           \
@@ -74,6 +74,11 @@ int rt_launch_recommend2(const int32_t *d_rptr, const int32_t *d_ridx, const flo
 int rt_gram_rows_selected(const int32_t *d_ccol, const int32_t *d_cidx, const float *d_cval, int64_t nnz, const int32_t *d_rptr,
                           const int32_t *d_ridx, const float *d_rval, const int32_t *d_row_slot, float *d_G, int64_t ldg,
                           cudaStream_t st);
+namespace rt {
+// tensor-core head of the Gram matrix (gram_tc.cu): *h_head = rows taken (0 = not applicable / does not pay)
+int gram_head_tc(int n_users, int n_items, const int *d_cptr, const int *d_cidx, const float *d_cval, int64_t nnz,
+                 const int *d_rptr, const int *d_pidx, const int *d_orig_of, float *d_Gp, int64_t ldgp, int *h_head, cudaStream_t st);
+}
 extern "C" int rt_csr_split(int32_t n_rows, const int32_t *d_ptr, const int32_t *d_idx, int32_t base,
                             int32_t range_width, int32_t n_ranges, int32_t *d_seg, void *stream);
 namespace rt {

@@ -658,6 +658,9 @@ using namespace rt;
         rt::count_launch(2);                                                                       \
     } while (0)
 
+static int g_last_head = 0;
+extern "C" int32_t rt_gram_last_head(void) { return g_last_head; }
+
 // block_mode = 0: part owns a contiguous row slab [h_cuts[part], h_cuts[part + 1]) balanced by multiply-adds, written
 // at its global rows of an I-row buffer.  block_mode = 1: block-cyclic ownership of 64-row blocks, the buffer holds only
 // the rows of this part (blk_local_row); no cost pass, no host synchronisation, h_cuts unused.
@@ -665,6 +668,7 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
                            const float *d_cval, const int32_t *d_rptr, const int32_t *d_ridx, const float *d_rval,
                            int64_t nnz, int32_t part, int32_t n_parts, float *d_Gp, int64_t ldgp, int32_t *d_rank_of,
                            int32_t *d_orig_of, int32_t *h_cuts, int block_mode, void *stream) {
+    g_last_head = 0;
     RT_ARG(n_users > 0 && n_items > 0 && nnz >= 0 && nnz < (1ll << 31), "shape");
     RT_ARG(n_parts >= 1 && part >= 0 && part < n_parts, "part / n_parts");
     RT_ARG(d_cptr && d_rptr && d_Gp && ldgp >= n_items && d_rank_of && d_orig_of && (h_cuts || block_mode), "null pointer / ldgp");
@@ -773,6 +777,14 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
         h_cuts[n_parts] = I;
         row_begin = h_cuts[part];
         row_end = h_cuts[part + 1];
+    }
+    // ---- dense head on the tensor cores (single-GPU form): the sparse kernel then starts below it ------------
+    if (n_parts == 1 && !block_mode && rt::option(rt::OPT_GRAM_HEAD) != 0 && rt::option(rt::OPT_GRAM_IMPL) != 1) {
+        int head = 0;
+        const int rc = rt::gram_head_tc(n_users, I, d_cptr, d_cidx, d_cval, nnz, d_rptr, P.pidx, d_orig_of, d_Gp, ldgp, &head, st);
+        if (rc) return rc;
+        if (head > row_begin) row_begin = head < row_end ? head : row_end;
+        g_last_head = head;
     }
     // ---- lower triangle ----------------------------------------------------------------------------
     if (row_end > row_begin) {

@@ -299,6 +299,48 @@ def test_gram_row_sort_all_row_lengths():
             assert np.array_equal(got, ref), (I, longest, impl)
 
 
+@pytest.mark.parametrize("rating", ["int", "half", "cont", "big"])
+def test_gram_head_on_tensor_cores_is_exact(rating):
+    """gram_tc.cu: the 2,048 x 2,048 corner of the most popular items as a tcgen05 SYRK over a bf16 copy of X.  Taken only
+    when the values are exact in bf16 and every partial sum is exact in fp32 (integer and half-integer ratings): the whole
+    matrix is then bit-identical to the sparse kernel's and to scipy's.  Continuous ratings, or values whose sums could
+    pass 2^24 units, keep the sparse kernel."""
+    from rtrec_b200 import _lib, device as D
+    U, I, N = 20000, 3000, 4_000_000
+    u, i, ts, r = synth_events(U, I, N, seed=31, rating="int")
+    X = sp.csc_matrix((np.ones(len(u), np.float32), (u, i)), shape=(U, I))
+    X.sum_duplicates()
+    rng = np.random.default_rng(7)
+    if rating == "int":
+        X.data[:] = rng.integers(1, 6, X.nnz)
+    elif rating == "half":
+        X.data[:] = rng.integers(-2, 11, X.nnz) * 0.5          # negative and explicit zero entries included
+    elif rating == "big":
+        X.data[:] = rng.integers(1, 200, X.nnz)                # exact in bf16, but the largest diagonal entry passes 2^24
+    else:
+        X.data[:] = rng.uniform(0.5, 5.0, X.nnz)
+    dX = D.DeviceMatrix.from_scipy(X)
+    lib = _lib.load()
+    G1 = D.gram_full(dX)
+    taken = int(lib.rt_gram_last_head())
+    assert taken == (2048 if rating in ("int", "half") else 0), taken
+    D.set_option("gram_head", 0)
+    try:
+        G0 = D.gram_full(dX)
+        assert int(lib.rt_gram_last_head()) == 0
+    finally:
+        D.set_option("gram_head", 1)
+    import torch
+    if taken:
+        assert torch.equal(G0, G1)
+        sel = np.unique(np.concatenate([rng.integers(0, I, 200), np.argsort(-np.diff(X.indptr))[:100]]))
+        ref = np.asarray((X[:, sel].T.astype(np.float64) @ X.astype(np.float64)).todense())
+        got = G1[D.to_dev(sel, np.int64)][:, :I].cpu().numpy().astype(np.float64)
+        assert np.array_equal(got, ref)
+    else:
+        assert float((G0 - G1).abs().max()) <= 2e-6 * float(G0.max())   # (float atomics: two runs differ in the last bits)
+
+
 def test_predict_family_matches_scipy(golden):
     """predict / predict_selected / predict_all (slim_elastic.py:566-626) against scipy on the golden W: same float32
     sums (ascending source item), dense and sparse output forms, errors as in the reference."""
