@@ -17,7 +17,8 @@ sys.path.insert(0, ROOT)
 import bench
 
 GROUPS = {   # phase of bench.py -> kernels that make it up (first capture of each is used)
-    "gram": ["gram_lower_kernel", "gram_mirror_kernel", "gram_unpermute_kernel", "gram_pull_cols_kernel"],
+    "gram": ["gram_lower_kernel", "gram_head_tc_kernel", "gh_densify_kernel", "gram_mirror_kernel", "gram_unpermute_kernel",
+             "gram_pull_cols_kernel", "row_sort_bitmap_kernel", "row_sort_small_kernel", "entry_pos_kernel"],
     "solve": ["slim_solve_warp_kernel", "slim_solve_kernel", "live_prefilter_kernel"],
     "recommend": ["recommend_tc_kernel", "recommend_tcfix_kernel", "recommend3_kernel", "recommend_sparse_kernel"],
 }
