@@ -561,7 +561,7 @@ def roofline_of(c, args, phase_ms, gram_bytes, solve_bytes, rec_bytes, rec_key="
 
 def finish_line(c, args, line):
     if c.rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if c.world > 1:
         c.dist.destroy_process_group()
 
@@ -1037,10 +1037,26 @@ def run_reference(args):
                 "port ingests ~25x faster than the reference's per-event Python loop (profiles/r3_ref_calibration.json)",
         "wall_s": round(time.perf_counter() - t_all0, 1),
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # Libraries write to file descriptor 1 behind Python's back (NCCL announces its version there): keep the original stdout
+    # for the JSON line and send everything else that lands on fd 1 to stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
