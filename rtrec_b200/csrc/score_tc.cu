@@ -319,13 +319,16 @@ __global__ void tc_scan_kernel(const float *__restrict__ vals, int64_t n, int *_
 // light rows + merge (CUDA cores), one CTA per query
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int FX_NT = 256;
-constexpr int FX_SLOTS = 4096;
-constexpr int FX_CAP = 2560;          // light entries a user may have (table load <= 0.625)
 constexpr int FX_CAND = 64;           // candidates kept for the final selection (tensor-core lists + surviving cells)
 constexpr double FX_SCALE = 4294967296.0;   // 2^32 fixed point
+// Two configurations of the same kernel.  The kernel is a chain of dependent loads and barriers per user (~10 us), so what
+// counts is how many users are in flight: the SMALL table (<= 1,280 light entries, <= 128 light items: 91 % of the users at
+// the ML-20M shape) needs 27 KB per CTA = 8 CTAs per SM instead of 3; users beyond it are put on a list and taken by a second
+// launch with the BIG table (<= 2,560 entries, <= 1,024 items); users beyond that go to the exact kernel.
+constexpr int FX_SLOTS_BIG = 4096, FX_CAP_BIG = 2560, FX_ROWS_BIG = 1024;
+constexpr int FX_SLOTS_SMALL = 2048, FX_CAP_SMALL = 1280, FX_ROWS_SMALL = 128;
 
-constexpr int FX_ROWS = 1024;         // light items of one user's row that can be staged
-
+template <int FX_SLOTS, int FX_ROWS>
 struct FxShared {
     unsigned long long val[FX_SLOTS];
     int key[FX_SLOTS];
@@ -344,33 +347,34 @@ struct FxShared {
     int red_s[FX_NT / 32];
 };
 
-__device__ __forceinline__ int fx_hash(int j) { return (int)(((unsigned)j * 2654435761u) >> 20) & (FX_SLOTS - 1); }
+// the table of one user uses the first `mask + 1` slots (a power of two >= twice the user's light entries, at least 256): the
+// median user has 250 light entries, and clearing and scanning all 4,096 slots for everybody was most of the kernel's time
+__device__ __forceinline__ int fx_hash(int j, int mask) { return (int)(((unsigned)j * 2654435761u) >> 20) & mask; }
 
+template <int FX_SLOTS, int FX_CAP, int FX_ROWS, bool DEFER>
 __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
     const int *__restrict__ rptr, const int *__restrict__ ridx, const float *__restrict__ rval, const int *__restrict__ users,
     int n_query, const int *__restrict__ wrptr, const int *__restrict__ wridx, const float *__restrict__ wrval,
     const int *__restrict__ heavy_of, const float *__restrict__ wd, const float *__restrict__ colmax, int n_items, int k,
     int filter, int dense_mode, const int *__restrict__ tc_ids, const float *__restrict__ tc_scores,
     int *__restrict__ out_ids, float *__restrict__ out_scores, int *__restrict__ out_cnt, int *__restrict__ fallback,
-    int *__restrict__ next_query) {
+    int *__restrict__ next_query, int *__restrict__ work_list, int *__restrict__ work_count) {
+    // DEFER: every query is visited, the ones that do not fit this configuration are appended to work_list (work_count).
+    // !DEFER with work_list: only the queries of work_list[0 .. *work_count) are visited.
     extern __shared__ __align__(16) unsigned char fx_raw[];
-    FxShared &S = *reinterpret_cast<FxShared *>(fx_raw);
+    using Shared = FxShared<FX_SLOTS, FX_ROWS>;
+    Shared &S = *reinterpret_cast<Shared *>(fx_raw);
+    if (!DEFER && work_list) n_query = *work_count;
     __shared__ int s_q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_q = atomicAdd(next_query, 1);
         __syncthreads();
-        const int q = s_q;
-        if (q >= n_query) break;
+        if (s_q >= n_query) break;
+        const int q = (!DEFER && work_list) ? work_list[s_q] : s_q;
         const int u = users[q];
         const int r0 = rptr[u], r1 = rptr[u + 1];
-        {   // clear the table with 16-byte stores
-            uint4 *kv = reinterpret_cast<uint4 *>(S.key);
-            uint4 *vv = reinterpret_cast<uint4 *>(S.val);
-            for (int s = tid; s < FX_SLOTS / 4; s += FX_NT) kv[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-            for (int s = tid; s < FX_SLOTS / 2; s += FX_NT) vv[s] = make_uint4(0u, 0u, 0u, 0u);
-        }
         if (tid == 0) { S.n_heavy_u = 0; S.n_cand = 0; S.n_light = 0; S.fallback = 0; S.n_rows = 0; S.staged = 0ull; }
         __syncthreads();
         // ---- pass 1: one coalesced sweep over the row: heavy items (ascending, ordered compaction) and the light rows
@@ -402,18 +406,34 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
             __syncthreads();
         }
         const int n_rows = (int)(S.staged >> 32);
-        if (n_rows > FX_ROWS) {         // more light items than can be staged: the exact kernel scores this user
-            if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
+        if (n_rows > FX_ROWS) {         // more light items than can be staged: the big configuration / the exact kernel
+            if (tid == 0) {
+                if (DEFER) work_list[atomicAdd(work_count, 1)] = q;
+                else { fallback[q] = 1; out_cnt[q] = 0; }
+            }
             continue;
         }
         if (tid == 0) { S.lpre[n_rows] = (int)(S.staged & 0xffffffffull); S.n_light = (int)(S.staged & 0xffffffffull); }
         __syncthreads();
         const int n_light = S.n_light;
-        if (n_light > FX_CAP) {      // the table would overflow: the exact kernel scores this user
-            if (tid == 0) { fallback[q] = 1; out_cnt[q] = 0; }
+        if (n_light > FX_CAP) {      // the table would overflow: the big configuration / the exact kernel
+            if (tid == 0) {
+                if (DEFER) work_list[atomicAdd(work_count, 1)] = q;
+                else { fallback[q] = 1; out_cnt[q] = 0; }
+            }
             continue;
         }
         const int nh = min(S.n_heavy_u, TC_KH);
+        int tsize = 256;
+        while (tsize < 2 * n_light && tsize < FX_SLOTS) tsize <<= 1;   // (n_light <= FX_CAP: load <= 0.625 at the full size)
+        const int mask = tsize - 1;
+        {   // clear the table with 16-byte stores
+            uint4 *kv = reinterpret_cast<uint4 *>(S.key);
+            uint4 *vv = reinterpret_cast<uint4 *>(S.val);
+            for (int s = tid; s < tsize / 4; s += FX_NT) kv[s] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            for (int s = tid; s < tsize / 2; s += FX_NT) vv[s] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
         // ---- pass 2: every light entry -> table, one entry per thread and step (64-bit fixed-point sums: the result does
         // not depend on the order of the adds)
         for (int e = tid; e < n_light; e += FX_NT) {
@@ -422,11 +442,11 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
             const int ge = S.la[lo] + (e - S.lpre[lo]);
             const int j = wridx[ge];
             const float add = __fmul_rn(S.lx[lo], wrval[ge]);
-            int slot = fx_hash(j);
+            int slot = fx_hash(j, mask);
             for (;;) {
                 const int prev = atomicCAS(&S.key[slot], -1, j);
                 if (prev == -1 || prev == j) break;
-                slot = (slot + 1) & (FX_SLOTS - 1);
+                slot = (slot + 1) & mask;
             }
             atomicAdd(&S.val[slot], (unsigned long long)__double2ll_rn((double)add * FX_SCALE));
         }
@@ -456,17 +476,17 @@ __global__ void __launch_bounds__(FX_NT) recommend_tcfix_kernel(
         // tensor-core candidates that are also table cells are superseded by the cell (which carries the light part)
         if (tid < 32 && S.ci[tid] >= 0) {
             const int j = S.ci[tid];
-            int slot = fx_hash(j);
+            int slot = fx_hash(j, mask);
             for (;;) {
                 const int kk = S.key[slot];
                 if (kk == -1) break;
                 if (kk == j) { S.cs[tid] = -1.0f; break; }
-                slot = (slot + 1) & (FX_SLOTS - 1);
+                slot = (slot + 1) & mask;
             }
         }
         // ---- pass 4: table cells.  Heavy part <= x1 * colmax[j] (every term is >= 0): most cells cannot reach the threshold
         // and are dropped after one load; the others get their heavy part (fp32, ascending item order) from the dense rows
-        for (int s = tid; s < FX_SLOTS; s += FX_NT) {
+        for (int s = tid; s < tsize; s += FX_NT) {
             const int j = S.key[s];
             if (j < 0) continue;
             const float lpart = (float)((double)(long long)S.val[s] / FX_SCALE);
@@ -633,17 +653,34 @@ extern "C" int rt_slim_recommend_tc(const int32_t *d_rptr, const int32_t *d_ridx
     RT_CHECK_LAUNCH();
     int *d_next = (int *)rt::scratch(SCR_MISC, 256);
     if (!d_next) return RT_ERR_CUDA;
-    d_next += 48;
-    RT_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), st));
+    d_next += 48;                       // [0] queue of the small configuration, [1] of the big one, [2] length of the deferred list
+    int *d_list = (int *)rt::scratch(SCR_SCORE, ((size_t)n_query + 64) * sizeof(int));
+    if (!d_list) return RT_ERR_CUDA;
+    RT_CUDA(cudaMemsetAsync(d_next, 0, 4 * sizeof(int), st));
     RT_CUDA(cudaMemsetAsync(d_fallback, 0, sizeof(int) * (size_t)n_query, st));
-    const size_t fsmem = sizeof(FxShared);
-    RT_CUDA(cudaFuncSetAttribute(recommend_tcfix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    int fgrid = rt::sm_count() * 3;
-    if (fgrid > n_query) fgrid = n_query;
-    recommend_tcfix_kernel<<<fgrid, FX_NT, fsmem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of,
-                                                      d_wd, d_wd + (size_t)n_heavy * n_items, n_items, k, filter_interacted,
-                                                      mode == RT_TOPK_DENSE ? 1 : 0, d_tc_ids, d_tc_scores, d_out_ids, d_out_scores,
-                                                      d_out_cnt, d_fallback, d_next);
+    const float *colmax = d_wd + (size_t)n_heavy * n_items;
+    const int dense = mode == RT_TOPK_DENSE ? 1 : 0;
+    {
+        auto kern = recommend_tcfix_kernel<FX_SLOTS_SMALL, FX_CAP_SMALL, FX_ROWS_SMALL, true>;
+        const size_t fsmem = sizeof(FxShared<FX_SLOTS_SMALL, FX_ROWS_SMALL>);
+        RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        int fgrid = rt::sm_count() * 8;
+        if (fgrid > n_query) fgrid = n_query;
+        kern<<<fgrid, FX_NT, fsmem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of, d_wd, colmax,
+                                          n_items, k, filter_interacted, dense, d_tc_ids, d_tc_scores, d_out_ids, d_out_scores, d_out_cnt,
+                                          d_fallback, d_next, d_list, d_next + 2);
+        RT_CHECK_LAUNCH();
+    }
+    {
+        auto kern = recommend_tcfix_kernel<FX_SLOTS_BIG, FX_CAP_BIG, FX_ROWS_BIG, false>;
+        const size_t fsmem = sizeof(FxShared<FX_SLOTS_BIG, FX_ROWS_BIG>);
+        RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        int fgrid = rt::sm_count() * 3;
+        if (fgrid > n_query) fgrid = n_query;
+        kern<<<fgrid, FX_NT, fsmem, st>>>(d_rptr, d_ridx, d_rval, d_users, n_query, d_wrptr, d_wridx, d_wrval, d_heavy_of, d_wd, colmax,
+                                          n_items, k, filter_interacted, dense, d_tc_ids, d_tc_scores, d_out_ids, d_out_scores, d_out_cnt,
+                                          d_fallback, d_next + 1, d_list, d_next + 2);
+    }
     RT_CHECK_LAUNCH();
     return RT_OK;
 }
