@@ -164,37 +164,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
             const int quad = warp & 3;
             const int half = (warp - 2) >> 2;
             const int row = quad * 32 + lane;
-            // ---- X_h of the 128 users -> swizzled A tile(s): one user at a time per warp, lanes stride over its CSR row
-            for (int uu = 0; uu < 16; ++uu) {
-                const int r = quad * 32 + half * 16 + uu;
-                const int q = blk * TC_M + r;
-                if (lane < 8) {
+            // ---- X_h of the 128 users -> swizzled A tile(s).  Each warp fills the rows of 16 users: rows zeroed first, row
+            // bounds fetched by 16 lanes at once, then one user at a time with four independent 32-entry batches in flight
+            // (index -> heavy slot is a dependent load: without the batching this phase was 14 % of the kernel's samples)
+            const int rbase = quad * 32 + half * 16;
 #pragma unroll
-                    for (int xa = 0; xa < SX; ++xa)
-                        *reinterpret_cast<uint4 *>(sA + xa * TC_TILE_BYTES + r * 128 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
-                }
-                __syncwarp();
-                if (q < P.n_query) {
-                    const int u = P.users[q];
-                    for (int p = P.rptr[u] + lane; p < P.rptr[u + 1]; p += 32) {
-                        const int h = P.heavy_of[P.ridx[p]];
-                        if (h >= 0) {
-                            const float x = P.rval[p];
-                            const int off = tc_sw_off(r, h);
-                            const __nv_bfloat16 x0 = __float2bfloat16_rn(x);
-                            *reinterpret_cast<__nv_bfloat16 *>(sA + off) = x0;
-                            if (SX == 3) {
-                                const float r1 = x - __bfloat162float(x0);
-                                const __nv_bfloat16 x1 = __float2bfloat16_rn(r1);
-                                const __nv_bfloat16 x2 = __float2bfloat16_rn(r1 - __bfloat162float(x1));
-                                *reinterpret_cast<__nv_bfloat16 *>(sA + TC_TILE_BYTES + off) = x1;
-                                *reinterpret_cast<__nv_bfloat16 *>(sA + 2 * TC_TILE_BYTES + off) = x2;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
+            for (int xa = 0; xa < SX; ++xa)
+                for (int z = lane; z < 16 * 8; z += 32)
+                    *reinterpret_cast<uint4 *>(sA + xa * TC_TILE_BYTES + (rbase + (z >> 3)) * 128 + (z & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            int my_a = 0, my_b = 0;
+            if (lane < 16 && blk * TC_M + rbase + lane < P.n_query) {
+                const int u = P.users[blk * TC_M + rbase + lane];
+                my_a = P.rptr[u]; my_b = P.rptr[u + 1];
             }
+            __syncwarp();
+            auto put = [&](int r, int h, float x) {
+                const int off = tc_sw_off(r, h);
+                const __nv_bfloat16 x0 = __float2bfloat16_rn(x);
+                *reinterpret_cast<__nv_bfloat16 *>(sA + off) = x0;
+                if (SX == 3) {
+                    const float r1 = x - __bfloat162float(x0);
+                    const __nv_bfloat16 x1 = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 x2 = __float2bfloat16_rn(r1 - __bfloat162float(x1));
+                    *reinterpret_cast<__nv_bfloat16 *>(sA + TC_TILE_BYTES + off) = x1;
+                    *reinterpret_cast<__nv_bfloat16 *>(sA + 2 * TC_TILE_BYTES + off) = x2;
+                }
+            };
+            for (int uu = 0; uu < 16; ++uu) {
+                const int r = rbase + uu;
+                const int ra = __shfl_sync(0xffffffffu, my_a, uu), rb = __shfl_sync(0xffffffffu, my_b, uu);
+                for (int p = ra + lane; p < rb; p += 128) {
+                    int it_[4], h_[4];
+                    float x_[4];
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) {
+                        const bool in = p + 32 * z < rb;
+                        it_[z] = in ? P.ridx[p + 32 * z] : -1;
+                        x_[z] = in ? P.rval[p + 32 * z] : 0.0f;
+                    }
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) h_[z] = it_[z] >= 0 ? P.heavy_of[it_[z]] : -1;
+#pragma unroll
+                    for (int z = 0; z < 4; ++z)
+                        if (h_[z] >= 0) put(r, h_[z], x_[z]);
+                }
+            }
+            __syncwarp();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full);
@@ -208,7 +223,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
             const bool live = q < P.n_query;
             int r_cur = 0, r_end = 0;
             if (live && P.filter) { const int u = P.users[q]; r_cur = P.rptr[u]; r_end = P.rptr[u + 1]; }
-            int nxt = r_cur < r_end ? P.ridx[r_cur] : 0x7fffffff;     // next interacted item of this user
+            // the next four interacted items of this user: the load that refills the window is issued three items before its
+            // value is needed, so the cursor walk below does not wait for global memory in (nearly) every tile
+            auto rd = [&](int p) { return p < r_end ? P.ridx[p] : 0x7fffffff; };
+            int n0 = rd(r_cur), n1 = rd(r_cur + 1), n2 = rd(r_cur + 2), n3 = rd(r_cur + 3);
             float *ls = list_s + half * TC_KLIST * TC_M + row;
             int *li = list_i + half * TC_KLIST * TC_M + row;
             int n = 0;
@@ -219,20 +237,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) recommend_tc_kernel(const __gri
                 const int t0 = t * TC_N;
                 // interacted items of this tile (own half) as two 32-bit masks; the row is ascending: a cursor walks it once
                 uint32_t ma = 0, mb = 0;
-                while (nxt < t0 + TC_N) {
-                    const int c = nxt - t0 - half * 64;
+                while (n0 < t0 + TC_N) {
+                    const int c = n0 - t0 - half * 64;
                     const uint32_t bit = 1u << (c & 31);
                     ma |= (c >> 5) == 0 ? bit : 0u; mb |= (c >> 5) == 1 ? bit : 0u;
+                    n0 = n1; n1 = n2; n2 = n3;
+                    n3 = rd(r_cur + 4);
                     ++r_cur;
-                    nxt = r_cur < r_end ? P.ridx[r_cur] : 0x7fffffff;
                 }
                 mbar_wait(acc_full(b), (g / TC_ACC) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * TC_N + half * 64);
+                // both 32-column chunks of this warp's half are requested before the wait: one TMEM round trip per tile
+                uint32_t va[32], vb[32];
+                tmem_ld32_nowait(taddr, va);
+                tmem_ld32_nowait(taddr + 32u, vb);
+                tmem_wait_ld();
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+                    uint32_t (&v)[32] = cc == 0 ? va : vb;
                     const int col0 = t0 + half * 64 + cc * 32;
                     if (P.dbg && live) {
 #pragma unroll
