@@ -321,6 +321,54 @@ class CpuPort:
             picks.append(rng.choice(dec, min(per_decile_any, len(dec)), replace=False))
         return np.unique(np.concatenate(picks)).astype(np.int32)
 
+    def _float64_check(self, Wd, res, cols, sel_dev, limit=8):
+        """Up to ``limit`` non-trivial columns solved by sklearn's ElasticNet in float64 (same hyper-parameters, same random
+        sequence; features restricted to the device's candidate list, or in all-features mode to the Cauchy-Schwarz
+        candidates, outside which every solution is zero: DESIGN.md section 3).  With ~1e6 samples per inner product the
+        float32 reference itself is percent-level off the float64 solution; the device keeps its solver state in float64."""
+        import warnings
+        from sklearn.linear_model import ElasticNet
+        X64 = self.Xc.astype(np.float64).tocsc()
+        U = X64.shape[0]
+        a_thr = 0.1 * 0.1 * U
+        feats_all = None
+        if not self.nn:
+            d = np.asarray(X64.multiply(X64).sum(axis=0)).ravel()
+            order = np.argsort(-d)
+            top1, top2 = d[order[0]], (d[order[1]] if len(d) > 1 else 0.0)
+            other = np.where(np.arange(len(d)) == order[0], top2, top1)
+            feats_all = np.flatnonzero(d * other > a_thr * a_thr)
+        worst_dev, worst_ref, n = 0.0, 0.0, 0
+        for t, j in enumerate(cols):
+            rows, vals = res[t]
+            a, b = Wd.indptr[j], Wd.indptr[j + 1]
+            if not (len(rows) and np.abs(vals).max() >= 1e-3) and not (b > a and np.abs(Wd.data[a:b]).max() >= 1e-3):
+                continue
+            if n >= limit:
+                break
+            a0, a1 = X64.indptr[j], X64.indptr[j + 1]
+            y = np.zeros(U); y[X64.indices[a0:a1]] = X64.data[a0:a1]
+            keep = X64.data[a0:a1].copy()
+            X64.data[a0:a1] = 0.0
+            feats = feats_all if feats_all is not None else sel_dev[t][sel_dev[t] >= 0]
+            en = ElasticNet(alpha=0.1, l1_ratio=0.1, fit_intercept=False, precompute=True, max_iter=100, copy_X=False, tol=1e-4,
+                            positive=True, random_state=43, selection="random")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                en.fit(X64[:, feats], y)
+            X64.data[a0:a1] = keep
+            w64 = np.zeros(self.I); w64[feats] = en.coef_
+            ref = np.zeros(self.I); ref[rows] = vals
+            dev = np.zeros(self.I); dev[Wd.indices[a:b]] = Wd.data[a:b]
+            scale = max(float(np.abs(w64).max()), 1e-30)
+            worst_dev = max(worst_dev, float(np.abs(dev - w64).max()) / scale)
+            worst_ref = max(worst_ref, float(np.abs(ref - w64).max()) / scale)
+            n += 1
+        return {"columns": n, "worst_rel_err_device_vs_float64_sklearn": worst_dev,
+                "worst_rel_err_float32_reference_vs_float64_sklearn": worst_ref,
+                "note": "the float32 reference arithmetic, not the device, is what is off at this sample count (DESIGN.md section 6)"
+                        if worst_dev <= worst_ref else "device further from float64 than the reference"}
+
     def parity(self, W_dev, cols, sel_dev=None, rec_users=None, rec_lists=None):
         """Device W against this port on ``cols``.  With feature selection the port is given the DEVICE's candidate lists
         (``sel_dev``), as the parity tests do: exact ties between integer feature scores at the cut are resolved by numpy's
@@ -352,6 +400,10 @@ class CpuPort:
             else:
                 small_abs.append(err)
         big = np.asarray(big)
+        f64 = None
+        if len(big) and float(big.max()) > 1e-3:
+            # the bar looks violated: is it the device or the float32 reference arithmetic?  Same sklearn solver in float64
+            f64 = self._float64_check(Wd, res, cols, sel_dev)
         out = {"columns_compared": int(len(cols)), "columns_nontrivial": int(n_nontriv),
                "columns_max_coef_ge_1e-3": int(len(big)),
                "frac_within_1e-4": round(float((big <= 1e-4).mean()), 5) if len(big) else None,
@@ -362,6 +414,8 @@ class CpuPort:
                "candidate_sets_differ_of_64": sets_differ,
                "bar": "north_star: W within 1e-4 relative (of the column maximum); flips = one-sweep stop-test differences; "
                       "columns with coefficients < 1e-3: absolute 1e-5 (DESIGN.md section 6, tests/helpers.py)"}
+        if f64 is not None:
+            out["float64_check"] = f64
         if rec_users is not None:
             exp = self._rec_cache
             same = 0
