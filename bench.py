@@ -552,7 +552,8 @@ def fit_phases(c, args, X, op, mark):
         # owner-rows fit: no full Gram exchange (None = CUDA IPC unavailable on this node, agreed by all ranks)
         res = P.fit_owner_rows(X, cfg, rank=rank, world=world, marks=mark)
     if res is None:
-        G = P.gram_sharded(X, rank=rank, world=world, exchange="nccl" if args.exchange == "nccl" else "p2p", marks=mark)
+        G = P.gram_sharded(X, rank=rank, world=world, exchange="nccl" if args.exchange == "nccl" else "p2p", marks=mark,
+                           live_cfg=cfg if world == 1 else None)   # as SLIMElastic._fit_device does for a bulk fit
         if world > 1 and args.scoring == "query":
             tg = P.item_stride(X.n_items, rank, world)   # interleaved targets: balanced whatever the id order
         else:

@@ -494,6 +494,16 @@ int rt_eval_metrics(const int32_t *d_ids, const int32_t *d_cnt, int32_t n_query,
  * kernel, a test hook for the overflow fallback).  Returns RT_ERR_ARG for an unknown name. */
 int rt_set_option(const char *name, int32_t value);
 
+/* rt_gram_finish_rowmax for a Gram matrix that only ONE bulk fit with feature selection will read: when cfg says that
+ * targets without a live coordinate are skipped (nn > 0, skip_trivial, positive, nonneg), a row whose off-diagonal maximum
+ * is not above alpha * l1_ratio * n_samples gets only its diagonal entry written -- the solver skips such a target
+ * (rt_fit_config.rowmax_ptr) and, G being symmetric, the item can be nobody's live coordinate.  The other entries of
+ * those rows keep whatever d_G held.  *h_live_only = 1 when rows were left out.  rt_slim_solve on this matrix must be
+ * called with the same cfg (with rowmax_ptr = d_rowmax), without candidate lists in or out. */
+int rt_gram_finish_live(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                        const int32_t *d_orig_of, float *d_G, int64_t ldg, float *d_rowmax,
+                        const rt_fit_config *cfg, int32_t *h_has_rowmax, int32_t *h_live_only, void *stream);
+
 /* Rows of the Gram matrix the last rt_gram_lower call of this process computed on the tensor cores (0 or 2048). */
 int32_t rt_gram_last_head(void);
 

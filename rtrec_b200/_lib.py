@@ -66,6 +66,7 @@ PROTOTYPES = {
     "rt_gram_lower": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, C.POINTER(_I32), _P]),
     "rt_gram_finish": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P]),
     "rt_gram_finish_rowmax": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P, C.POINTER(_I32), _P]),
+    "rt_gram_finish_live": (C.c_int, [_I32, _P, _I64, _P, _P, _P, _I64, _P, C.POINTER(FitConfig), C.POINTER(_I32), C.POINTER(_I32), _P]),
     "rt_gram_block_rows": (C.c_int, [_I32, _I32, _I32, C.POINTER(_I32), C.POINTER(_I32)]),
     "rt_gram_lower_blocks": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
     "rt_gram_pull_cols": (C.c_int, [_I32, _P, _I32, _I32, _I64, _P]),

@@ -542,11 +542,14 @@ __global__ void __launch_bounds__(256) gram_pull_mirror_v4_kernel(GramPeers P, f
 __global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__restrict__ Gp, int64_t ldp, int n_rows, int n,
                                                               const int *__restrict__ rank_of, const int *__restrict__ orig_of,
                                                               float *__restrict__ G, int64_t ld, int stage,
-                                                              float *__restrict__ rowmax) {
+                                                              float *__restrict__ rowmax, int live_only, double live_above) {
     // rowmax (optional, staged mode with orig_of): largest off-diagonal entry of every row, by item id -- the solver uses it
-    // to finish targets without a live coordinate without reading their Gram rows again
+    // to finish targets without a live coordinate without reading their Gram rows again.
+    // live_only (with rowmax): a row whose off-diagonal maximum is not above live_above is a row the solver never reads
+    // (its target is trivial, and it can be nobody's live coordinate: G is symmetric) -- only its diagonal entry is written.
     extern __shared__ __align__(16) float row_s[];
     __shared__ float s_red[32];
+    __shared__ int s_skip;
     const int NT = blockDim.x;
     for (int jp = blockIdx.x; jp < n_rows; jp += gridDim.x) {
         const float *src = Gp + (size_t)jp * ldp;
@@ -566,7 +569,17 @@ __global__ void __launch_bounds__(1024) gram_unpermute_kernel(const float *__res
                 float m2 = threadIdx.x < (NT >> 5) ? s_red[threadIdx.x] : -INFINITY;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-                if (threadIdx.x == 0) rowmax[orig_of[jp]] = m2;
+                if (threadIdx.x == 0) {
+                    rowmax[orig_of[jp]] = m2;
+                    s_skip = live_only && !((double)m2 > live_above);
+                }
+            }
+            if (live_only && rowmax && orig_of) {
+                __syncthreads();
+                if (s_skip) {
+                    if (threadIdx.x == 0) dst[orig_of[jp]] = row_s[jp];
+                    continue;
+                }
             }
 #pragma unroll 4
             for (int x = threadIdx.x; x < n; x += NT) dst[x] = row_s[rank_of[x]];
@@ -842,7 +855,7 @@ extern "C" int rt_gram_lower_blocks(int32_t n_users, int32_t n_items, const int3
 
 static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
                             const int32_t *d_orig_of, float *d_G, int64_t ldg, cudaStream_t st, float *d_rowmax = nullptr,
-                            int32_t *h_has_rowmax = nullptr) {
+                            int32_t *h_has_rowmax = nullptr, int live_only = 0, double live_above = 0.0) {
     const size_t row_bytes = sizeof(float) * (size_t)n_items;
     const int stage = row_bytes + 2048 <= (size_t)rt::smem_optin() ? 1 : 0;
     const size_t smem = stage ? row_bytes : 0;
@@ -853,10 +866,27 @@ static int launch_unpermute(int32_t n_items, const float *d_Gp, int64_t ldgp, co
     int grid = rt::sm_count() * per_sm;
     if (grid > n_items) grid = n_items;
     gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_Gp, ldgp, n_items, n_items, d_rank_of, d_orig_of, d_G, ldg, stage,
-                                                    stage ? d_rowmax : nullptr);
+                                                    stage ? d_rowmax : nullptr, (stage && d_rowmax) ? live_only : 0, live_above);
     RT_CHECK_LAUNCH();
     if (h_has_rowmax) *h_has_rowmax = (stage && d_rowmax) ? 1 : 0;
     return RT_OK;
+}
+
+extern "C" int rt_gram_finish_live(int32_t n_items, float *d_Gp, int64_t ldgp, const int32_t *d_rank_of,
+                                   const int32_t *d_orig_of, float *d_G, int64_t ldg, float *d_rowmax,
+                                   const rt_fit_config *cfg, int32_t *h_has_rowmax, int32_t *h_live_only, void *stream) {
+    RT_ARG(n_items > 0 && d_Gp && d_G && d_rank_of && d_orig_of && ldgp >= n_items && ldg >= n_items && d_rowmax && h_has_rowmax && cfg && h_live_only, "arguments");
+    RT_ARG(d_Gp != d_G, "rt_gram_finish is not in-place");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned nt = (unsigned)((n_items + 63) / 64);
+    gram_mirror_kernel<<<nt * (nt + 1) / 2, 256, 0, st>>>(d_Gp, n_items, ldgp);
+    RT_CHECK_LAUNCH();
+    // the same conditions and the same threshold as the solver's trivial-target rule (solve.cu: A.skip_trivial, A.a)
+    const int live_only = (cfg->nn > 0 && cfg->skip_trivial && cfg->positive && cfg->nonneg) ? 1 : 0;
+    const double a = (double)(float)(cfg->alpha * cfg->l1_ratio * (double)cfg->n_samples);
+    const int rc = launch_unpermute(n_items, d_Gp, ldgp, d_rank_of, d_orig_of, d_G, ldg, st, d_rowmax, h_has_rowmax, live_only, a);
+    *h_live_only = (rc == RT_OK && live_only && *h_has_rowmax) ? 1 : 0;
+    return rc;
 }
 
 extern "C" int rt_gram_block_rows(int32_t n_items, int32_t n_parts, int32_t part, int32_t *h_rows_alloc, int32_t *h_rows_own) {
@@ -904,7 +934,7 @@ extern "C" int rt_gram_unpermute_rows(int32_t n_rows, int32_t n_items, const flo
     if (per_sm > 2) per_sm = 2;
     int grid = rt::sm_count() * per_sm;
     if (grid > n_rows) grid = n_rows;
-    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_slab, ldgp, n_rows, n_items, d_rank_of, nullptr, d_rows, ldg, stage, nullptr);
+    gram_unpermute_kernel<<<grid, 1024, smem, st>>>(d_slab, ldgp, n_rows, n_items, d_rank_of, nullptr, d_rows, ldg, stage, nullptr, 0, 0.0);
     RT_CHECK_LAUNCH();
     return RT_OK;
 }

@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 128 ? 8 : 2) slim_solve_kernel(S
         if (t >= A.n_targets) break;
         if (A.only_flagged && !A.only_flagged[t]) continue;
         const int j = A.targets[t];
-        if (nnmode && A.skip_trivial && A.item_flag && !A.item_flag[j]) {     // pruned fit: no row, zero column
+        if (nnmode && A.skip_trivial && ((A.rowmax && !((double)A.rowmax[j] > A.a)) || (A.item_flag && !A.item_flag[j]))) {
+            // no live coordinate (row maximum from rt_gram_finish_rowmax / _live), or pruned fit: no row -- the zero column
             if (tid == 0) {
                 A.out_off[t] = (int64_t)t * NU; A.out_cnt[t] = 0;
                 if (A.stats) { A.stats[(size_t)t * 4 + 0] = 0; A.stats[(size_t)t * 4 + 1] = 0; A.stats[(size_t)t * 4 + 2] = 1; A.stats[(size_t)t * 4 + 3] = 0; }

@@ -297,7 +297,10 @@ def block_targets(orig_of, n_items: int, part: int, n_parts: int):
     return orig_of.long()[jp].to(t.int32)
 
 
-def gram_finish(L: GramLower, out=None):
+def gram_finish(L: GramLower, out=None, live_cfg: Optional[FitConfig] = None):
+    """Mirror + back to item ids.  ``live_cfg``: the matrix is for ONE ``solve`` call with this configuration and without
+    candidate lists in or out; rows the solver provably never reads (bulk fit with feature selection: targets without a
+    live coordinate) then get only their diagonal entry (rt_gram_finish_live) and ``out._rt_live_only`` is set."""
     t = require_cuda()
     I = L.Gp.shape[0]
     if out is None:
@@ -306,15 +309,21 @@ def gram_finish(L: GramLower, out=None):
     # and rides along on the tensor (``solve`` hands it to the solver, which then skips trivial targets without a read)
     rowmax = empty(I, t.float32)
     has = C.c_int32(0)
-    check(_lib.load().rt_gram_finish_rowmax(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, ptr(rowmax),
-                                            C.byref(has), stream_ptr()), "rt_gram_finish_rowmax")
+    live = C.c_int32(0)
+    if live_cfg is not None:
+        check(_lib.load().rt_gram_finish_live(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, ptr(rowmax),
+                                              C.byref(live_cfg), C.byref(has), C.byref(live), stream_ptr()), "rt_gram_finish_live")
+    else:
+        check(_lib.load().rt_gram_finish_rowmax(I, ptr(L.Gp), I, ptr(L.rank_of), ptr(L.orig_of), ptr(out), I, ptr(rowmax),
+                                                C.byref(has), stream_ptr()), "rt_gram_finish_rowmax")
     out._rt_rowmax = rowmax if has.value else None
+    out._rt_live_only = bool(live.value)
     return out
 
 
-def gram_full(X: DeviceMatrix, out=None):
+def gram_full(X: DeviceMatrix, out=None, live_cfg: Optional[FitConfig] = None):
     """Dense symmetric item-item Gram matrix G in item ids (K3, third generation)."""
-    return gram_finish(gram_lower(X), out=out)
+    return gram_finish(gram_lower(X), out=out, live_cfg=live_cfg)
 
 
 def gram_cols(X: DeviceMatrix, j_begin: int = 0, j_end: Optional[int] = None, out=None):
@@ -392,6 +401,8 @@ def solve(G, n_items: int, targets, cfg: FitConfig, sel_in=None, want_sel: bool 
                                         ptr(sel_in), ptr(rng), rng.numel(), ptr(sel_out), ptr(off), ptr(cnt), ptr(rows),
                                         ptr(vals), cap, C.byref(needed), ptr(stats), stream_ptr())
         else:
+            if getattr(G, "_rt_live_only", False) and (sel_in is not None or want_sel or not (cfg.nn > 0 and cfg.skip_trivial)):
+                raise ValueError("this Gram matrix holds only the rows of a bulk fit with feature selection (gram_finish live_cfg)")
             rowmax = getattr(G, "_rt_rowmax", None)
             if rowmax is not None and not cfg.rowmax_ptr:
                 cfg = FitConfig.from_buffer_copy(cfg)

@@ -154,7 +154,10 @@ class SLIMElastic:
                 res = P.gather_solve_results(part, ctx[1])
                 targets = res.targets.cpu().numpy()
         if res is None:
-            G = D.gram_full(X) if X.nnz > 0 else D.gram(X)
+            # this G is read by the one solve below: with feature selection in a bulk fit, rows the solver never touches
+            # (targets without a live coordinate) are not written back to item order
+            live = cfg if (sel_in is None and not self.keep_fit_details) else None
+            G = D.gram_full(X, live_cfg=live) if X.nnz > 0 else D.gram(X)
             sel_dev = None
             if sel_in is not None and cfg.nn > 0:
                 sel_dev = D.to_dev(np.ascontiguousarray(sel_in, dtype=np.int32).reshape(-1))

@@ -235,7 +235,7 @@ class PeerSlabs:
         self.ptrs, self.own = [], 0
 
 
-def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchange: str = "p2p", marks=None):
+def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchange: str = "p2p", marks=None, live_cfg=None):
     """Item-item Gram matrix on every rank of the node: each rank computes its row slab of the rank-space
     lower triangle; ``exchange="p2p"`` pulls the other slabs over NVLink inside the mirror kernel
     (rt_gram_finish_p2p), ``exchange="nccl"`` broadcasts the slabs and mirrors locally."""
@@ -243,7 +243,7 @@ def gram_sharded(X: D.DeviceMatrix, *, rank: int, world: int, group=None, exchan
     if world <= 1:
         L = D.gram_lower(X)
         mark("gram_lower")
-        G = D.gram_finish(L)
+        G = D.gram_finish(L, live_cfg=live_cfg)    # (single GPU: see D.gram_finish for what live_cfg promises)
         mark("gram_finish")
         return G
     slabs = PeerSlabs.get(X.n_items, rank, world, group) if exchange == "p2p" else None

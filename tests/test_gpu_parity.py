@@ -539,6 +539,63 @@ def test_pruned_fit_equals_dense_path():
     assert np.abs(Wpn.data - Wdn.data).max() <= 1e-4 * np.abs(Wdn.data).max()
 
 
+def test_live_rows_only_gram_gives_the_same_w():
+    """rt_gram_finish_live: for a bulk fit with feature selection the Gram rows of items without an entry above the L1
+    threshold are never read by the solver (trivial targets are skipped, and by symmetry such an item is nobody's live
+    coordinate), so only their diagonal is written.  The unwritten entries are NaN here: W must not notice, and must be
+    bit-identical to the fit on the full matrix."""
+    import torch
+    from rtrec_b200 import device as D
+    from rtrec_b200.models.internal.slim_elastic import SLIMElastic
+    U, I, N = 30000, 1500, 200000
+    u, i, ts, r = synth_events(U, I, N, seed=17, rating="cont")
+    dX = D.DeviceMatrix.from_scipy(sp.csc_matrix((r.astype(np.float32), (u, i)), shape=(U, I)))
+    op = SLIMElastic({"nn_feature_selection": 20})
+    cfg = op._config(dX)
+    tg = torch.arange(I, dtype=torch.int32, device="cuda")
+    L = D.gram_lower(dX)
+    Gp_keep = L.Gp.clone()
+    G_full = D.gram_finish(L)
+    res_full = D.solve(G_full, I, tg, cfg)
+    W_full = D.w_merge(None, I, res_full).to_scipy_csc()
+    L.Gp.copy_(Gp_keep)                                     # (the finish pass mirrors Gp in place)
+    out = torch.full((I, I), float("nan"), dtype=torch.float32, device="cuda")
+    G_live = D.gram_finish(L, out=out, live_cfg=cfg)
+    assert G_live._rt_live_only
+    untouched = torch.isnan(G_live).any(dim=1)
+    trivial = ~(G_live._rt_rowmax.double() > float(np.float32(0.1 * 0.1 * U)))
+    assert int(untouched.sum()) > I // 10 and bool((untouched == trivial).all())
+    assert torch.equal(torch.diagonal(G_live), torch.diagonal(G_full))
+    assert torch.equal(G_live[~untouched], G_full[~untouched])
+    for impl in (2, 1, 3):                                  # warp kernel, CTA kernel for every target, forced hand-overs
+        D.set_option("solve_impl", impl)
+        try:
+            res = D.solve(G_live, I, tg, cfg)
+        finally:
+            D.set_option("solve_impl", 2)
+        W = D.w_merge(None, I, res).to_scipy_csc()
+        assert W.nnz == W_full.nnz and W.nnz > 0 and np.array_equal(W.indptr, W_full.indptr)
+        assert np.array_equal(W.indices, W_full.indices) and np.array_equal(W.data, W_full.data), impl
+        assert np.isfinite(W.data).all()
+    # such a matrix cannot serve a merge fit or a call with candidate lists
+    with pytest.raises(ValueError):
+        D.solve(G_live, I, tg, op._config(dX, into_empty_w=False))
+    with pytest.raises(ValueError):
+        D.solve(G_live, I, tg, cfg, want_sel=True)
+    # without feature selection, or for a merge, nothing is left out
+    assert not D.gram_full(dX, live_cfg=SLIMElastic({})._config(dX))._rt_live_only
+    assert not D.gram_full(dX, live_cfg=op._config(dX, into_empty_w=False))._rt_live_only
+    # and the operator takes the path by itself (the pruned fit, which would come first, is switched off here: its Gram rows
+    # are accumulated with float atomics and agree to rounding only)
+    D.set_option("fit_pruned", 0)
+    try:
+        op.fit(dX)
+    finally:
+        D.set_option("fit_pruned", 1)
+    Wo = sp.csc_matrix(op.item_similarity)
+    assert np.array_equal(Wo.indptr, W_full.indptr) and np.array_equal(Wo.data, W_full.data)
+
+
 @pytest.mark.parametrize("nn", [20, None])
 def test_trivial_columns_shortcut_gives_the_same_w(nn):
     """Targets whose Gram row has no entry above the L1 threshold are zero before the first sweep.  Bulk fits return them
