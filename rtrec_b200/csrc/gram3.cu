@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(256) row_sort_bitmap_kernel(int n_users, int n
 // the exact multiply-add count of every rank-column (sum of prefix lengths) for the multi-GPU partition
 __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict__ rank_of, const int *__restrict__ cptr,
                                  const int *__restrict__ cidx, const int *__restrict__ rptr, const int *__restrict__ pidx,
-                                 int *__restrict__ cpos, unsigned long long *__restrict__ cost, int blk_parts, int blk_me) {
+                                 int *__restrict__ cpos, unsigned long long *__restrict__ cost, int blk_parts, int blk_me,
+                                 int head) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = e < nnz;
     int jp = -1;
@@ -219,6 +220,7 @@ __global__ void entry_pos_kernel(int n_items, int64_t nnz, const int *__restrict
         jp = rank_of[lo];
         // block-cyclic mode: positions are only needed for the columns this part owns (cost == nullptr there)
         if (blk_parts > 0 && ((jp >> 6) % blk_parts) != blk_me) return;
+        if (jp < head) return;     // column computed on the tensor cores (head > 0 only without a cost pass)
         const int u = cidx[e];
         const int a = rptr[u];
         int l2 = a, h2 = rptr[u + 1];
@@ -764,10 +766,18 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
         int rc = rt_csr_split(n_users, d_rptr, P.pidx, 0, RW, R, P.hseg, stream);
         if (rc) return rc;
     }
+    // ---- dense head on the tensor cores (single-GPU form): the sparse kernel then starts below it, and the entries of the
+    // head columns (most of the matrix: the popular items) need no position
+    int head = 0;
+    if (n_parts == 1 && !block_mode && rt::option(rt::OPT_GRAM_HEAD) != 0 && rt::option(rt::OPT_GRAM_IMPL) != 1) {
+        const int rc = rt::gram_head_tc(n_users, I, d_cptr, d_cidx, d_cval, nnz, d_rptr, P.pidx, d_orig_of, d_Gp, ldgp, &head, st);
+        if (rc) return rc;
+        g_last_head = head;
+    }
     const bool by_cost = n_parts > 1 && !block_mode;
     if (by_cost) RT_CUDA(cudaMemsetAsync(P.cost, 0, sizeof(unsigned long long) * ((size_t)I + 1), st));
     entry_pos_kernel<<<(unsigned)((nnz + bs - 1) / bs), bs, 0, st>>>(I, nnz, d_rank_of, d_cptr, d_cidx, d_rptr, P.pidx, P.cpos,
-                                                                    by_cost ? P.cost : nullptr, blk_parts, part);
+                                                                    by_cost ? P.cost : nullptr, blk_parts, part, head);
     RT_CHECK_LAUNCH();
     chunk_count_kernel<<<(I + bs - 1) / bs, bs, 0, st>>>(I, d_orig_of, d_cptr, P.n_chunks, blk_parts, part);
     RT_CHECK_LAUNCH();
@@ -791,14 +801,7 @@ static int gram_lower_impl(int32_t n_users, int32_t n_items, const int32_t *d_cp
         row_begin = h_cuts[part];
         row_end = h_cuts[part + 1];
     }
-    // ---- dense head on the tensor cores (single-GPU form): the sparse kernel then starts below it ------------
-    if (n_parts == 1 && !block_mode && rt::option(rt::OPT_GRAM_HEAD) != 0 && rt::option(rt::OPT_GRAM_IMPL) != 1) {
-        int head = 0;
-        const int rc = rt::gram_head_tc(n_users, I, d_cptr, d_cidx, d_cval, nnz, d_rptr, P.pidx, d_orig_of, d_Gp, ldgp, &head, st);
-        if (rc) return rc;
-        if (head > row_begin) row_begin = head < row_end ? head : row_end;
-        g_last_head = head;
-    }
+    if (head > row_begin) row_begin = head < row_end ? head : row_end;
     // ---- lower triangle ----------------------------------------------------------------------------
     if (row_end > row_begin) {
         RT_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
