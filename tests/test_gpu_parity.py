@@ -593,7 +593,10 @@ def test_live_rows_only_gram_gives_the_same_w():
     finally:
         D.set_option("fit_pruned", 1)
     Wo = sp.csc_matrix(op.item_similarity)
-    assert np.array_equal(Wo.indptr, W_full.indptr) and np.array_equal(Wo.data, W_full.data)
+    # (a second Gram pass: the shared-memory float atomics of the sparse kernel add in another order, continuous ratings
+    # differ in the last bits)
+    assert np.array_equal(Wo.indptr, W_full.indptr) and np.array_equal(Wo.indices, W_full.indices)
+    assert np.abs(Wo.data - W_full.data).max() <= 1e-5 * np.abs(W_full.data).max()
 
 
 @pytest.mark.parametrize("nn", [20, None])
